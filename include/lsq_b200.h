@@ -1,0 +1,160 @@
+/*
+ * lsq_b200.h -- C ABI of libtorchlsq_b200.so: the B200-native (sm_100a) LSQ+ fake-quantize path.
+ *
+ * This is the drop-in boundary for the ONE hot path of torchlsq 2.1 (DeadAt0m/LSQFakeQuantize-
+ * PyTorch): what the reference's `torchlsq/_C.so` does behind `torch.ops.torchlsq.*` for CUDA
+ * tensors.  Plain pointers and sizes only -- no torch types.  Citations are file:line under
+ * /root/reference/torchlsq/.
+ *
+ * Conventions
+ *   - every tensor pointer is a DEVICE pointer to a contiguous buffer viewed as
+ *     (outer, C, inner): per-tensor ops use C == 1; per-channel `axis` splits the shape into
+ *     outer = prod(shape[:axis]), C = shape[axis], inner = prod(shape[axis+1:]).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - functions never allocate, never synchronise, never throw.  Return 0 on success, a
+ *     negative LSQB200_ERR_* for argument errors, or a positive cudaError_t.
+ *     lsqb200_last_error() returns a thread-local message for the last non-zero return.
+ *   - scale/shift are read ON DEVICE (the reference syncs the host with scale[0].item(),
+ *     csrc/ops/cuda/lsq_cuda.cu:52-53,120-121); |scale| is clamped to eps and 1/s formed
+ *     in-kernel with IEEE ops (csrc/ops/cuda/lsq_cuda.cu:54-55, csrc/ops/kernels/lsq_kernel.h:157-159).
+ *   - arithmetic contract: csrc/ops/kernels/lsq_kernel.h:6-145 as compiled by nvcc for the
+ *     reference CUDA build (x*inv_s+zp and (r-zp)*s-x are single FMAs); see DESIGN.md section 3.
+ */
+#ifndef LSQ_B200_H
+#define LSQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSQB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LSQB200_API __attribute__((visibility("default")))
+#else
+#define LSQB200_API
+#endif
+
+/* element types of x / y / grad / grad_x, and of scale / shift / grad_scale / grad_shift */
+#define LSQB200_F32 0
+#define LSQB200_F16 1
+#define LSQB200_BF16 2
+
+#define LSQB200_OK 0
+#define LSQB200_ERR_ARG (-1)        /* null pointer, negative size, bad flag */
+#define LSQB200_ERR_DTYPE (-2)      /* unsupported (x dtype, param dtype) pair */
+#define LSQB200_ERR_WORKSPACE (-3)  /* workspace missing / too small / misaligned */
+#define LSQB200_ERR_PLAN (-4)       /* bad plan handle or segment list */
+
+/* Scalar arguments of the four backend ops, in schema order
+ * (csrc/ops/lsq.cpp:138-145: quant_min, quant_max, type_min, type_max, use_grad_scaling,
+ * grad_scaler, sym, eval_mode, init_mode). */
+typedef struct lsqb200_qargs {
+    int64_t quant_min, quant_max, type_min, type_max;
+    double grad_scaler;
+    int32_t use_grad_scaling; /* gs = grad_scaler / sqrt(numel * quant_max), lsq_cuda.cu:124,274 */
+    int32_t sym;              /* symmetric: grad_shift == 0, lsq_kernel.h:85 */
+    int32_t eval_mode;        /* grad_scale = grad_shift = 0, lsq_kernel.h:126-145 */
+    int32_t init_mode;        /* learned init: y = x, gx = g, g' = 2(xfq - x), lsq_kernel.h:13,35,57 */
+} lsqb200_qargs;
+
+/* ---- library info ------------------------------------------------------------------------ */
+/* LSQB200_ABI_VERSION the library was built with. */
+LSQB200_API int lsqb200_abi_version(void);
+/* CUDA_VERSION the kernels were compiled with; replaces quantops::cuda_version(),
+ * csrc/torchlsq.cpp:25-31 (`torch.ops.torchlsq._cuda_version`). */
+LSQB200_API int64_t lsqb200_cuda_version(void);
+LSQB200_API const char* lsqb200_last_error(void);
+/* Fixed size of the reduction workspace every backward / stats call needs.  The caller
+ * allocates it once per (device, stream), ZERO-FILLS IT ONCE, and never touches it again:
+ * kernels leave it zeroed.  Two calls may not use the same workspace concurrently. */
+LSQB200_API size_t lsqb200_workspace_bytes(void);
+
+/* ---- per-tensor: replaces lsq_forward_per_tensor_impl / lsq_backward_per_tensor_impl,
+ *      csrc/ops/cuda/lsq_cuda.cu:18-61 and :64-143 ------------------------------------------ */
+LSQB200_API int lsqb200_fwd_tensor(const void* x, void* y, const void* scale, const void* shift,
+                       int64_t numel, int xdtype, int pdtype,
+                       const lsqb200_qargs* q, void* stream);
+/* gx may be NULL (x needs no grad: 2 reads, no write).  gscale/gshift: 1 element of pdtype. */
+LSQB200_API int lsqb200_bwd_tensor(const void* grad, const void* x, void* gx,
+                       const void* scale, const void* shift, void* gscale, void* gshift,
+                       int64_t numel, int xdtype, int pdtype,
+                       const lsqb200_qargs* q, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* ---- per-channel: replaces lsq_forward_per_channel_impl / lsq_backward_per_channel_impl,
+ *      csrc/ops/cuda/lsq_cuda.cu:147-199 and :202-297.  scale/shift/gscale/gshift: C elements.
+ *      gs uses the WHOLE tensor's numel (CUDA formula, lsq_cuda.cu:274). ---------------------- */
+LSQB200_API int lsqb200_fwd_channel(const void* x, void* y, const void* scale, const void* shift,
+                        int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype,
+                        const lsqb200_qargs* q, void* stream);
+LSQB200_API int lsqb200_bwd_channel(const void* grad, const void* x, void* gx,
+                        const void* scale, const void* shift, void* gscale, void* gshift,
+                        int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype,
+                        const lsqb200_qargs* q, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ---- mu +- 3 sigma weight initialisation: replaces the torch.mean / torch.std passes of
+ *      LSQFakeQuantizer._init_weights, quantized/modules/observers.py:329-337.
+ *      scale_out: float[C]; C == 1 gives the whole-tensor statistic. ------------------------- */
+LSQB200_API int lsqb200_weight_init_stats(const void* w, float* scale_out,
+                              int64_t outer, int64_t C, int64_t inner, int xdtype,
+                              int64_t quant_min, int64_t quant_max,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- multi-tensor plans: one launch for many fake-quant sites (the 54 ResNet-50 weights, or
+ *      every site of a step).  Semantics per segment are exactly those of the calls above. --- */
+typedef struct lsqb200_segment {
+    const void* x;      /* input */
+    void* y;            /* forward output (may be NULL if the plan is only run backward) */
+    const void* grad;   /* upstream gradient (backward) */
+    void* gx;           /* grad_x output, may be NULL */
+    const void* scale;  /* [C] (or [1] when per_channel == 0) */
+    const void* shift;
+    void* gscale;       /* [C] or [1], pdtype -- e.g. a slice of the data-parallel flat grad buffer */
+    void* gshift;
+    int64_t outer, C, inner; /* per-tensor: outer = 1, C = 1, inner = numel */
+    int32_t xdtype, pdtype;
+    int32_t per_channel;
+    int32_t reserved;
+    lsqb200_qargs q;
+} lsqb200_segment;
+
+typedef struct lsqb200_plan lsqb200_plan; /* opaque */
+
+/* Copies the segment table to the device and sizes a private workspace (this call allocates
+ * and synchronises; the run calls below do neither).  All segments must share xdtype/pdtype
+ * alignment class; mixed dtypes are allowed. */
+LSQB200_API int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan** out);
+LSQB200_API int lsqb200_plan_forward(lsqb200_plan* plan, void* stream);
+LSQB200_API int lsqb200_plan_backward(lsqb200_plan* plan, void* stream);
+/* float scale_out per channel written to each segment's `gscale` slot is NOT used here:
+ * stats go to `scale_out[offset_of_segment ...]`, offsets = running sum of C (or 1). */
+LSQB200_API int lsqb200_plan_weight_init_stats(lsqb200_plan* plan, float* scale_out, void* stream);
+LSQB200_API int lsqb200_plan_destroy(lsqb200_plan* plan);
+/* number of kernel launches one plan_forward / plan_backward issues (for launch accounting) */
+LSQB200_API int lsqb200_plan_launches(const lsqb200_plan* plan, int backward);
+
+/* ---- introspection used by tests and bench.py ------------------------------------------- */
+typedef struct lsqb200_launch_info {
+    int32_t regime;       /* 0 = flat contiguous channel rows, 1 = strided rows */
+    int32_t vec;          /* elements per 128-bit access (1 = scalar fallback) */
+    int32_t threads;      /* CTA size */
+    int32_t splits;       /* CTAs per channel */
+    int64_t grid;         /* CTAs launched */
+    int64_t units_per_split;
+} lsqb200_launch_info;
+/* Geometry the library would pick for a (outer, C, inner) tensor; pure host computation. */
+LSQB200_API int lsqb200_query_launch(int64_t outer, int64_t C, int64_t inner, int xdtype, int backward,
+                         int aligned16, lsqb200_launch_info* out);
+/* Override tuning knobs (NULL / "" restores defaults).  Format "threads=256,unroll=4,occ=4,
+ * tile_kb=512".  For experiments; not part of the reference surface. */
+LSQB200_API int lsqb200_set_tuning(const char* spec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSQ_B200_H */

@@ -1,0 +1,427 @@
+// lsq_api.cu -- extern "C" entry points of libtorchlsq_b200.so (see include/lsq_b200.h).
+// Host code only: argument checks, launch geometry, kernel selection, launches.  No allocation
+// and no synchronisation on the per-call paths; plans allocate once at creation.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/lsq_b200.h"
+#include "lsq_host.h"
+
+using namespace lsqb200;
+
+namespace {
+
+thread_local std::string g_last_error;
+Tuning g_tuning;
+std::once_flag g_sm_once;
+
+int fail(int code, const char* msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
+    return (int)e;
+}
+
+const Tuning& tuning() {
+    std::call_once(g_sm_once, [] {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            g_tuning.sm_count = sms;
+        if (const char* env = std::getenv("LSQB200_TUNE")) lsqb200_set_tuning(env);
+    });
+    return g_tuning;
+}
+
+// (x dtype, param dtype) -> arithmetic mode; returns -1 when the pair is not supported
+int pick_mode(int xdt, int pdt) {
+    if (xdt == DT_F32 && pdt == DT_F32) return M_FP32;
+    if (xdt == DT_F16 && pdt == DT_F32) return M_FP32;
+    if (xdt == DT_F16 && pdt == DT_F16) return M_HALF_EXACT;   // reference-exact c10::Half semantics
+    if (xdt == DT_BF16 && (pdt == DT_F32 || pdt == DT_BF16)) return M_FP32;
+    return -1;
+}
+
+int check_q(const lsqb200_qargs* q) {
+    if (!q) return fail(LSQB200_ERR_ARG, "qargs is NULL");
+    return 0;
+}
+
+int bmode_of(const lsqb200_qargs* q) {
+    if (q->eval_mode) return q->init_mode ? B_EVAL_INIT : B_EVAL;
+    return q->init_mode ? B_INIT : B_NORMAL;
+}
+
+SegArgs seg_args(const void* x, void* y, const void* g, void* gx, const void* scale, const void* shift,
+                 void* gscale, void* gshift, int64_t outer, int64_t C, int64_t inner, int xdt, int pdt,
+                 int per_channel, const lsqb200_qargs* q) {
+    SegArgs a{};
+    a.x = x; a.y = y; a.g = g; a.gx = gx; a.scale = scale; a.shift = shift; a.gscale = gscale; a.gshift = gshift;
+    a.stats_out = nullptr;
+    a.outer = outer; a.C = C; a.inner = inner; a.xdtype = xdt; a.pdtype = pdt; a.per_channel = per_channel;
+    if (q) {
+        a.qmin = q->quant_min; a.qmax = q->quant_max; a.tmin = q->type_min; a.tmax = q->type_max;
+        a.grad_scaler = q->grad_scaler; a.use_grad_scaling = q->use_grad_scaling; a.sym = q->sym;
+    }
+    return a;
+}
+
+int launch(KernelFn k, const Seg& seg, const Seg* table, int nseg, long long tiles, long long grid, cudaStream_t st) {
+    if (grid <= 0) return 0;
+    if (grid > 2147483647LL) return fail(LSQB200_ERR_ARG, "tensor too large for one launch");
+    k<<<(unsigned)grid, kThreads, 0, st>>>(seg, table, nseg, tiles);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return 0;
+}
+
+size_t param_size(int pdt) { return pdt == DT_F32 ? 4 : 2; }
+
+int forward_common(const void* x, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
+                   int64_t inner, int xdt, int pdt, int per_channel, const lsqb200_qargs* q, void* stream) {
+    if (int r = check_q(q)) return r;
+    if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
+    if (xdt < 0 || xdt > 2 || pdt < 0 || pdt > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    const int mode = pick_mode(xdt, pdt);
+    if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
+    if (outer * C * inner == 0) return 0;
+    if (!x || !y || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    const bool al = is_aligned16(x) && is_aligned16(y);
+    const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, al, tuning());
+    SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
+    const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
+    KernelFn k = get_fwd_kernel(xdt, mode, g.vec > 1, q->init_mode != 0, g.group);
+    return launch(k, seg, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
+}
+
+int backward_common(const void* grad, const void* x, void* gx, const void* scale, const void* shift, void* gscale,
+                    void* gshift, int64_t outer, int64_t C, int64_t inner, int xdt, int pdt, int per_channel,
+                    const lsqb200_qargs* q, void* workspace, size_t wbytes, void* stream) {
+    if (int r = check_q(q)) return r;
+    if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
+    if (xdt < 0 || xdt > 2 || pdt < 0 || pdt > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    const int mode = pick_mode(xdt, pdt);
+    if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
+    if (!gscale || !gshift) return fail(LSQB200_ERR_ARG, "NULL grad_scale / grad_shift pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nslot = per_channel ? C : 1;
+    if (outer * C * inner == 0) {   // empty input: defined, all-zero parameter grads (reference returns its inputs, D13)
+        if (nslot > 0) {
+            cudaError_t e = cudaMemsetAsync(gscale, 0, nslot * param_size(pdt), st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(gshift, 0, nslot * param_size(pdt), st);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+        }
+        return 0;
+    }
+    if (!grad || !x || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    const bool al = is_aligned16(x) && is_aligned16(grad) && is_aligned16(gx);
+    const Geometry g = plan_geometry(outer, C, inner, xdt, K_BWD, al, tuning());
+    double* partials = nullptr;
+    unsigned* counters = nullptr;
+    if (g.splits > 1) {
+        if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u))
+            return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
+        counters = reinterpret_cast<unsigned*>(workspace);
+        partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kMaxCounters * 4);
+    }
+    SegArgs a = seg_args(x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, xdt, pdt, per_channel, q);
+    const Seg seg = make_seg(a, g, partials, counters, 0);
+    KernelFn k = get_bwd_kernel(xdt, mode, g.vec > 1, bmode_of(q), g.group);
+    return launch(k, seg, nullptr, 0, g.tiles, g.grid, st);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// plans
+// ---------------------------------------------------------------------------------------------
+struct lsqb200_plan {
+    struct Class {
+        KernelFn kernel = nullptr;
+        std::vector<Seg> host;
+        Seg* dev = nullptr;
+        long long tiles = 0, grid = 0;
+        int group = kThreads;
+    };
+    std::vector<Class> fwd, bwd, stats;
+    std::vector<lsqb200_segment> segs;
+    std::vector<long long> stats_offset;   // running sum of C (or 1) per segment
+    void* workspace = nullptr;             // counters + partials for every split segment
+    float** stats_slot = nullptr;
+    int device = 0;
+};
+
+namespace {
+
+using ClassKey = std::tuple<int, int, int, int, int>;   // xdtype, mode, vec?, variant (init / bmode), group
+
+int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& out, char* ws_base, size_t& ws_used,
+                  bool assign_ws) {
+    std::map<ClassKey, size_t> index;
+    const Tuning& tn = tuning();
+    for (size_t i = 0; i < p->segs.size(); i++) {
+        const lsqb200_segment& s = p->segs[i];
+        const int mode = pick_mode(s.xdtype, s.pdtype);
+        if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair in plan");
+        if (s.outer * s.C * s.inner == 0) continue;
+        bool al = is_aligned16(s.x);
+        if (kind == K_FWD) al = al && is_aligned16(s.y);
+        if (kind == K_BWD) al = al && is_aligned16(s.grad) && is_aligned16(s.gx);
+        Geometry g = plan_geometry(s.outer, s.C, s.inner, s.xdtype, kind, al, tn);
+        int variant = 0;
+        KernelFn k = nullptr;
+        if (kind == K_FWD) { variant = s.q.init_mode != 0; k = get_fwd_kernel(s.xdtype, mode, g.vec > 1, variant, g.group); }
+        else if (kind == K_BWD) { variant = bmode_of(&s.q); k = get_bwd_kernel(s.xdtype, mode, g.vec > 1, variant, g.group); }
+        else { k = get_stats_kernel(s.xdtype, g.vec > 1, g.group); }
+        const ClassKey key{s.xdtype, kind == K_STATS ? 0 : mode, g.vec > 1, variant, g.group};
+        auto it = index.find(key);
+        if (it == index.end()) {
+            it = index.emplace(key, out.size()).first;
+            out.emplace_back();
+            out.back().kernel = k;
+            out.back().group = g.group;
+        }
+        lsqb200_plan::Class& c = out[it->second];
+        double* partials = nullptr;
+        unsigned* counters = nullptr;
+        if (kind != K_FWD && g.splits > 1) {
+            const size_t need = (size_t)g.C * 4 + 16 + (size_t)g.tiles * 16;
+            if (assign_ws) {
+                counters = reinterpret_cast<unsigned*>(ws_base + ws_used);
+                partials = reinterpret_cast<double*>(ws_base + ws_used + (((size_t)g.C * 4 + 15) / 16) * 16);
+            }
+            ws_used += ((need + 15) / 16) * 16;
+        }
+        SegArgs a = seg_args(s.x, s.y, s.grad, s.gx, s.scale, s.shift, s.gscale, s.gshift, s.outer, s.C, s.inner,
+                             s.xdtype, s.pdtype, s.per_channel, &s.q);
+        Seg seg = make_seg(a, g, partials, counters, c.tiles);
+        seg.stats_out = nullptr;   // patched per run for stats
+        // tag for stats runs: remember which public segment this is (reuse chan_stride, unused by kernels)
+        seg.chan_stride = (long long)i;
+        c.host.push_back(seg);
+        c.tiles += g.tiles;
+    }
+    for (auto& c : out) {
+        const long long gpc = kThreads / c.group;
+        c.grid = (c.tiles + gpc - 1) / gpc;
+    }
+    return 0;
+}
+
+int upload_classes(std::vector<lsqb200_plan::Class>& cls) {
+    for (auto& c : cls) {
+        if (c.host.empty()) continue;
+        cudaError_t e = cudaMalloc(&c.dev, c.host.size() * sizeof(Seg));
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan table)");
+        e = cudaMemcpy(c.dev, c.host.data(), c.host.size() * sizeof(Seg), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(plan table)");
+    }
+    return 0;
+}
+
+int run_classes(std::vector<lsqb200_plan::Class>& cls, cudaStream_t st) {
+    for (auto& c : cls) {
+        if (c.host.empty()) continue;
+        if (int r = launch(c.kernel, c.host[0], c.dev, (int)c.host.size(), c.tiles, c.grid, st)) return r;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lsqb200_abi_version(void) { return LSQB200_ABI_VERSION; }
+int64_t lsqb200_cuda_version(void) { return (int64_t)CUDA_VERSION; }
+const char* lsqb200_last_error(void) { return g_last_error.c_str(); }
+size_t lsqb200_workspace_bytes(void) { return kWorkspaceBytes; }
+
+int lsqb200_set_tuning(const char* spec) {
+    const int sms = g_tuning.sm_count;
+    g_tuning = Tuning();
+    g_tuning.sm_count = sms;
+    if (!spec || !*spec) return 0;
+    std::string s(spec);
+    size_t pos = 0;
+    while (pos < s.size()) {
+        size_t end = s.find(',', pos);
+        if (end == std::string::npos) end = s.size();
+        const std::string kv = s.substr(pos, end - pos);
+        const size_t eq = kv.find('=');
+        if (eq == std::string::npos) return fail(LSQB200_ERR_ARG, "tuning spec: expected key=value");
+        const std::string k = kv.substr(0, eq);
+        const int v = std::atoi(kv.c_str() + eq + 1);
+        if (k == "tiles_per_sm") g_tuning.tiles_per_sm = v;
+        else if (k == "max_tile_kb") g_tuning.max_tile_kb = v;
+        else if (k == "warp_units") g_tuning.warp_units = v;
+        else if (k == "min_iters") g_tuning.min_iters = v;
+        else if (k == "sm_count") g_tuning.sm_count = v;
+        else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
+        pos = end + 1;
+    }
+    if (g_tuning.tiles_per_sm < 1 || g_tuning.min_iters < 1 || g_tuning.sm_count < 1 || g_tuning.warp_units < 0) {
+        g_tuning = Tuning();
+        g_tuning.sm_count = sms;
+        return fail(LSQB200_ERR_ARG, "tuning spec: value out of range");
+    }
+    return 0;
+}
+
+int lsqb200_query_launch(int64_t outer, int64_t C, int64_t inner, int xdtype, int backward, int aligned16,
+                         lsqb200_launch_info* out) {
+    if (!out || outer < 0 || C < 0 || inner < 0 || xdtype < 0 || xdtype > 2) return fail(LSQB200_ERR_ARG, "bad argument");
+    const Geometry g = plan_geometry(outer, C, inner, xdtype, backward ? K_BWD : K_FWD, aligned16 != 0, tuning());
+    out->regime = g.regime; out->vec = g.vec; out->threads = kThreads; out->splits = g.splits;
+    out->grid = g.grid; out->units_per_split = g.units_per_split;
+    return 0;
+}
+
+int lsqb200_fwd_tensor(const void* x, void* y, const void* scale, const void* shift, int64_t numel, int xdtype,
+                       int pdtype, const lsqb200_qargs* q, void* stream) {
+    return forward_common(x, y, scale, shift, 1, 1, numel, xdtype, pdtype, 0, q, stream);
+}
+
+int lsqb200_bwd_tensor(const void* grad, const void* x, void* gx, const void* scale, const void* shift, void* gscale,
+                       void* gshift, int64_t numel, int xdtype, int pdtype, const lsqb200_qargs* q, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    return backward_common(grad, x, gx, scale, shift, gscale, gshift, 1, 1, numel, xdtype, pdtype, 0, q, workspace,
+                           workspace_bytes, stream);
+}
+
+int lsqb200_fwd_channel(const void* x, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
+                        int64_t inner, int xdtype, int pdtype, const lsqb200_qargs* q, void* stream) {
+    return forward_common(x, y, scale, shift, outer, C, inner, xdtype, pdtype, 1, q, stream);
+}
+
+int lsqb200_bwd_channel(const void* grad, const void* x, void* gx, const void* scale, const void* shift, void* gscale,
+                        void* gshift, int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype,
+                        const lsqb200_qargs* q, void* workspace, size_t workspace_bytes, void* stream) {
+    return backward_common(grad, x, gx, scale, shift, gscale, gshift, outer, C, inner, xdtype, pdtype, 1, q, workspace,
+                           workspace_bytes, stream);
+}
+
+int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, int64_t C, int64_t inner, int xdtype,
+                              int64_t quant_min, int64_t quant_max, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+    if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
+    if (xdtype < 0 || xdtype > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    if (quant_max <= quant_min) return fail(LSQB200_ERR_ARG, "quant_max must exceed quant_min");
+    if (outer * C * inner == 0) return 0;
+    if (!w || !scale_out) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    const Geometry g = plan_geometry(outer, C, inner, xdtype, K_STATS, is_aligned16(w), tuning());
+    double* partials = nullptr;
+    unsigned* counters = nullptr;
+    if (g.splits > 1) {
+        if (!workspace || workspace_bytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u))
+            return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
+        counters = reinterpret_cast<unsigned*>(workspace);
+        partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kMaxCounters * 4);
+    }
+    lsqb200_qargs q{};
+    q.quant_min = quant_min; q.quant_max = quant_max; q.type_min = quant_min; q.type_max = quant_max; q.grad_scaler = 1.0;
+    SegArgs a = seg_args(w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, outer, C, inner, xdtype, DT_F32,
+                         C > 1, &q);
+    a.stats_out = scale_out;
+    const Seg seg = make_seg(a, g, partials, counters, 0);
+    KernelFn k = get_stats_kernel(xdtype, g.vec > 1, g.group);
+    return launch(k, seg, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
+}
+
+int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan** out) {
+    if (!segs || nseg <= 0 || !out) return fail(LSQB200_ERR_PLAN, "empty segment list");
+    lsqb200_plan* p = new lsqb200_plan();
+    p->segs.assign(segs, segs + nseg);
+    cudaGetDevice(&p->device);
+    long long off = 0;
+    for (const auto& s : p->segs) {
+        if (s.outer < 0 || s.C < 0 || s.inner < 0 || s.xdtype < 0 || s.xdtype > 2 || s.pdtype < 0 || s.pdtype > 2) {
+            delete p;
+            return fail(LSQB200_ERR_PLAN, "bad segment (negative size or unknown dtype)");
+        }
+        p->stats_offset.push_back(off);
+        off += s.per_channel ? s.C : 1;
+    }
+    // pass 1: size the private workspace (backward and stats never run concurrently on one plan)
+    size_t need_b = 0, need_s = 0;
+    {
+        std::vector<lsqb200_plan::Class> tmp;
+        int r = build_classes(p, K_BWD, tmp, nullptr, need_b, false);
+        if (!r) { tmp.clear(); r = build_classes(p, K_STATS, tmp, nullptr, need_s, false); }
+        if (r) { delete p; return r; }
+    }
+    const size_t ws = need_b > need_s ? need_b : need_s;
+    if (ws) {
+        cudaError_t e = cudaMalloc(&p->workspace, ws);
+        if (e == cudaSuccess) e = cudaMemset(p->workspace, 0, ws);
+        if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc(plan workspace)"); }
+    }
+    size_t used = 0;
+    int r = build_classes(p, K_FWD, p->fwd, nullptr, used, false);
+    used = 0;
+    if (!r) r = build_classes(p, K_BWD, p->bwd, (char*)p->workspace, used, true);
+    used = 0;
+    if (!r) r = build_classes(p, K_STATS, p->stats, (char*)p->workspace, used, true);
+    if (!r) r = upload_classes(p->fwd);
+    if (!r) r = upload_classes(p->bwd);
+    if (r) { lsqb200_plan_destroy(p); return r; }
+    cudaDeviceSynchronize();
+    *out = p;
+    return 0;
+}
+
+int lsqb200_plan_forward(lsqb200_plan* plan, void* stream) {
+    if (!plan) return fail(LSQB200_ERR_PLAN, "NULL plan");
+    return run_classes(plan->fwd, (cudaStream_t)stream);
+}
+
+int lsqb200_plan_backward(lsqb200_plan* plan, void* stream) {
+    if (!plan) return fail(LSQB200_ERR_PLAN, "NULL plan");
+    return run_classes(plan->bwd, (cudaStream_t)stream);
+}
+
+int lsqb200_plan_weight_init_stats(lsqb200_plan* plan, float* scale_out, void* stream) {
+    if (!plan || !scale_out) return fail(LSQB200_ERR_PLAN, "NULL plan or output");
+    // tables are (re)uploaded with the output pointers patched in; this is an init-time call
+    for (auto& c : plan->stats) {
+        if (c.host.empty()) continue;
+        for (auto& s : c.host) s.stats_out = scale_out + plan->stats_offset[(size_t)s.chan_stride];
+        if (!c.dev) {
+            cudaError_t e = cudaMalloc(&c.dev, c.host.size() * sizeof(Seg));
+            if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan table)");
+        }
+        cudaError_t e = cudaMemcpyAsync(c.dev, c.host.data(), c.host.size() * sizeof(Seg), cudaMemcpyHostToDevice,
+                                        (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync(plan table)");
+    }
+    return run_classes(plan->stats, (cudaStream_t)stream);
+}
+
+int lsqb200_plan_launches(const lsqb200_plan* plan, int backward) {
+    if (!plan) return 0;
+    int n = 0;
+    for (const auto& c : (backward ? plan->bwd : plan->fwd)) n += !c.host.empty();
+    return n;
+}
+
+int lsqb200_plan_destroy(lsqb200_plan* plan) {
+    if (!plan) return 0;
+    for (auto* v : {&plan->fwd, &plan->bwd, &plan->stats})
+        for (auto& c : *v)
+            if (c.dev) cudaFree(c.dev);
+    if (plan->workspace) cudaFree(plan->workspace);
+    delete plan;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,621 @@
+// lsq_device.cuh -- sm_100a device code for the LSQ+ fake-quantize hot path.
+//
+// One kernel family serves per-tensor, per-channel and multi-tensor launches: a tensor is a
+// contiguous (outer, C, inner) box; a CTA owns one TILE = (channel c, split j) = a contiguous
+// slice of channel c's element space, so scale / shift / zero-point are CTA-uniform registers
+// and the backward's grad_scale / grad_shift partial sums stay in registers until one
+// warp-shuffle -> shared-memory -> (last-arriver, fixed-order) reduction per tile.
+//
+// Arithmetic contract (file:line under /root/reference/torchlsq/csrc/ops/):
+//   kernels/lsq_kernel.h:12-13    zp, forward value            -> fq_forward()
+//   kernels/lsq_kernel.h:33-36    clamped un-rounded xq, mask   -> fq_backward()
+//   kernels/lsq_kernel.h:56-61    xfq, learned-init grad, dS
+//   kernels/lsq_kernel.h:85-86    dB
+//   kernels/lsq_kernel.h:157-159  per-channel eps clamp + 1/s   -> make_chan()
+//   cuda/lsq_cuda.cu:52-55        per-tensor eps clamp + 1/s (host side in the reference)
+//   global_scope.h:39,51-52       nearbyint, fminf/fmaxf
+// nvcc fuses x*inv_s+zp and (r-zp)*s-x into FFMAs in the reference CUDA build (checked in its
+// sm_100a SASS); this file spells every operation with explicit-rounding intrinsics so that
+// exactly those two are fused and nothing else is.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lsqb200 {
+
+enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+// MODE: how the affine value v = x/s + zp is formed
+enum : int { M_FP32 = 0,        // fp32 internal math (fp32 tensors; fp16/bf16 tensors up-cast)
+             M_HALF_EXACT = 1 };// fp16 x with fp16 params: round to half after every operator (c10::Half)
+enum : int { B_NORMAL = 0, B_INIT = 1, B_EVAL = 2, B_EVAL_INIT = 3 };
+__host__ __device__ constexpr bool bmode_passthrough(int b) { return b == B_INIT || b == B_EVAL_INIT; }
+__host__ __device__ constexpr bool bmode_reduces(int b) { return b == B_NORMAL || b == B_INIT; }
+
+// ---------------------------------------------------------------------------------------------
+// Segment descriptor (one fake-quant site).  Passed by value for single launches, read from a
+// device table for multi-tensor plans.
+// ---------------------------------------------------------------------------------------------
+struct Seg {
+    const void* x;
+    void* y;
+    const void* g;
+    void* gx;
+    const void* scale;
+    const void* shift;
+    void* gscale;
+    void* gshift;
+    double* partials;      // [tiles_of_segment * 2] when splits > 1
+    unsigned* counters;    // [C] when splits > 1 (self-resetting tickets)
+    float* stats_out;      // weight-init: float[C]
+    long long C;
+    long long vpr;         // units per row (regime 1); huge for regime 0
+    long long row_stride;  // C * vpr, in units (regime 1)
+    long long chan_stride; // units between channel starts: vpr (regime 1); unused (regime 0)
+    long long inner;       // elements per row
+    long long chan_units;  // units in one channel's space (body only for regime 0)
+    long long units_per_split;
+    long long tile_begin;  // first global tile id of this segment (plans)
+    long long chan_elems;  // outer * inner (elements per channel), for stats
+    double gs;             // grad scale factor (already includes grad_scaler)
+    float qmin, qmax, tmin, tmax;
+    float stats_denom;     // 2^bitness
+    int splits;
+    int regime;            // 0: channel space contiguous (outer == 1), 1: strided rows
+    int per_channel;
+    int pdt;
+    int sym;
+    int vec;               // elements per unit actually used (1 or 16/sizeof(T))
+};
+
+// ---------------------------------------------------------------------------------------------
+// memory access policies
+// ---------------------------------------------------------------------------------------------
+enum : int { LD_DEFAULT = 0, LD_NC_NOALLOC = 1, LD_EVICT_FIRST = 2 };
+enum : int { ST_DEFAULT = 0, ST_CS = 1, ST_NOALLOC = 2 };
+
+template <int LD>
+__device__ __forceinline__ uint4 ld128(const void* p) {
+    uint4 r;
+    if (LD == LD_NC_NOALLOC)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (LD == LD_EVICT_FIRST)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else
+        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <int ST>
+__device__ __forceinline__ void st128(void* p, const uint4& v) {
+    if (ST == ST_CS)
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (ST == ST_NOALLOC)
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// element <-> float conversion; T is the storage type (float, __half, __nv_bfloat16)
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct ElemTraits;
+template <> struct ElemTraits<float> {
+    static constexpr int VEC = 4;
+    static __device__ __forceinline__ float to_f(float v) { return v; }
+    static __device__ __forceinline__ float from_f(float v) { return v; }
+    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[4]) {
+        f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
+        f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
+        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+    }
+};
+template <> struct ElemTraits<__half> {
+    static constexpr int VEC = 8;
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+            float2 t = __half22float2(h);
+            f[2 * i] = t.x; f[2 * i + 1] = t.y;
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+template <> struct ElemTraits<__nv_bfloat16> {
+    static constexpr int VEC = 8;
+    static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            f[2 * i] = __uint_as_float(w[i] << 16);
+            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        return make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+__device__ __forceinline__ float load_param(const void* p, long long i, int pdt) {
+    if (pdt == DT_F32) return reinterpret_cast<const float*>(p)[i];
+    if (pdt == DT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void store_param(void* p, long long i, int pdt, double v) {
+    if (pdt == DT_F32) reinterpret_cast<float*>(p)[i] = (float)v;
+    else if (pdt == DT_F16) reinterpret_cast<__half*>(p)[i] = __float2half_rn((float)v);
+    else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn((float)v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar math
+// ---------------------------------------------------------------------------------------------
+struct Chan {
+    float s, inv_s, zp;
+    float c_lo, c_hi;   // qmin - zp, qmax - zp (border multipliers of dS)
+    float qmin, qmax;
+};
+
+__device__ __forceinline__ float hround(float f) { return __half2float(__float2half_rn(f)); }
+
+template <int MODE>
+__device__ __forceinline__ Chan make_chan(float scale, float shift, const Seg& sg) {
+    Chan c;
+    const float a = fabsf(scale);
+    if (MODE == M_HALF_EXACT) {
+        const float eps = 0.0009765625f;                           // numeric_limits<c10::Half>::epsilon
+        c.s = sg.per_channel ? fmaxf(eps, a) : ((a < eps) ? eps : a);
+        c.inv_s = hround(__fdiv_rn(1.0f, c.s));
+        const float t = hround(__fmul_rn(-shift, c.inv_s));
+        c.zp = hround(rintf(fminf(sg.tmax, fmaxf(sg.tmin, t))));
+    } else {
+        const float eps = 1.1920928955078125e-07f;                 // numeric_limits<float>::epsilon
+        // per-tensor: std::max(|s|, eps) (NaN stays NaN); per-channel: fmaxf(eps, |s|)
+        c.s = sg.per_channel ? fmaxf(eps, a) : ((a < eps) ? eps : a);
+        c.inv_s = __fdiv_rn(1.0f, c.s);
+        const float t = __fmul_rn(-shift, c.inv_s);
+        c.zp = rintf(fminf(sg.tmax, fmaxf(sg.tmin, t)));
+    }
+    c.qmin = sg.qmin; c.qmax = sg.qmax;
+    c.c_lo = __fsub_rn(sg.qmin, c.zp);
+    c.c_hi = __fsub_rn(sg.qmax, c.zp);
+    return c;
+}
+
+template <int MODE>
+__device__ __forceinline__ float affine_v(float x, const Chan& c) {
+    if (MODE == M_HALF_EXACT) return hround(__fadd_rn(hround(__fmul_rn(x, c.inv_s)), c.zp));
+    return __fmaf_rn(x, c.inv_s, c.zp);
+}
+
+template <int MODE>
+__device__ __forceinline__ float fq_forward(float x, const Chan& c) {
+    const float v = affine_v<MODE>(x, c);
+    const float r = rintf(fminf(c.qmax, fmaxf(c.qmin, v)));       // max first: NaN -> qmin
+    return __fmul_rn(__fsub_rn(r, c.zp), c.s);
+}
+
+// returns dX (as float); accumulates the two fp32 terms (not yet multiplied by gs)
+template <int MODE, int BMODE>
+__device__ __forceinline__ float fq_backward(float g, float x, const Chan& c, float& accS, float& accB) {
+    const float v = affine_v<MODE>(x, c);
+    const float xq = fmaxf(fminf(v, c.qmax), c.qmin);             // min first: NaN -> qmax
+    const bool lt_hi = xq < c.qmax;
+    const bool mask = (c.qmin < xq) && lt_hi;
+    const float m = mask ? 1.0f : 0.0f;
+    const float dX = bmode_passthrough(BMODE) ? g : __fmul_rn(g, m);   // g*mask keeps -0 / NaN like the reference
+    if (bmode_reduces(BMODE)) {
+        const float r = rintf(xq);
+        const float t = __fsub_rn(r, c.zp);
+        const float d = __fmaf_rn(t, c.s, -x);                     // xfq - x, fused as in the reference build
+        const float gg = (BMODE == B_INIT) ? __fmul_rn(2.0f, d) : g;
+        const float border = __fmul_rn(gg, (xq <= c.qmin) ? c.c_lo : c.c_hi);
+        const float inner = __fmul_rn(__fmul_rn(gg, d), c.inv_s);
+        const float dS = mask ? inner : border;
+        const float dB = __fmul_rn(__fsub_rn(1.0f, m), gg);        // (!mask) * g'
+        accS = __fadd_rn(accS, dS);
+        accB = __fadd_rn(accB, dB);
+    }
+    return dX;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile bookkeeping.  A tile is owned by a GROUP of G threads: the whole CTA (G == THREADS) for
+// long channel slices, or one warp (G == 32) for short ones (e.g. conv-weight rows), so that
+// eight independent rows share a 256-thread CTA and reductions never leave the warp.
+// ---------------------------------------------------------------------------------------------
+template <int G, int THREADS>
+__device__ __forceinline__ void group_sync() {
+    if (G == 32) __syncwarp(); else __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// fixed-order group reduction of two doubles; result valid in group thread 0
+template <int G, int THREADS>
+__device__ __forceinline__ void group_sum2(double& a, double& b, double* sm /* [64] per CTA */) {
+    a = warp_sum(a); b = warp_sum(b);
+    if (G == 32) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    constexpr int NW = THREADS / 32;
+    if (lane == 0) { sm[w] = a; sm[32 + w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = lane < NW ? sm[lane] : 0.0;
+        b = lane < NW ? sm[32 + lane] : 0.0;
+        a = warp_sum(a); b = warp_sum(b);
+    }
+    __syncthreads();   // sm[] may be reused by the caller
+}
+
+// Copy this group's descriptor into shared memory (uniform broadcast reads afterwards).
+// Returns false when the group has no tile (grid round-up).
+template <int G, int THREADS>
+__device__ __forceinline__ bool stage_segment(const Seg& single, const Seg* table, int nseg,
+                                              long long gtile, long long total_tiles, Seg* dst_seg) {
+    if (gtile >= total_tiles) return false;      // whole group exits together (G == THREADS: never)
+    const int tg = threadIdx.x % G;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(dst_seg);
+    constexpr int NW = sizeof(Seg) / 4;
+    if (table == nullptr) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&single);
+        for (int i = tg; i < NW; i += G) dst[i] = src[i];
+    } else {
+        int lo = 0, hi = nseg - 1;                // last segment with tile_begin <= gtile
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid].tile_begin <= gtile) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&table[lo]);
+        for (int i = tg; i < NW; i += G) dst[i] = src[i];
+    }
+    group_sync<G, THREADS>();
+    return true;
+}
+
+// Walks the units [u0, u1) of one channel slice, G threads interleaved, yielding unit addresses.
+// Units are addressed as (row n, column col) with address = base + n*row_stride + col; regime 0
+// (contiguous channel) uses artificial rows of vpr = row_stride = 2^30 units, so all per-thread
+// state is 32-bit and one code path serves both regimes.
+struct Walker {
+    long long base, row_stride;
+    int n, col, dn, dcol, vpr;
+    unsigned left;            // units this thread still has to visit, in steps of G (tile-local)
+    template <int G>
+    __device__ __forceinline__ void init(const Seg& sg, long long u0, long long u1, long long base_unit, int tg) {
+        vpr = (int)sg.vpr; row_stride = sg.row_stride; base = base_unit;
+        const long long u = u0 + tg;
+        left = (u < u1) ? (unsigned)((u1 - u + G - 1) / G) : 0u;
+        const long long nn = u / vpr;
+        n = (int)nn; col = (int)(u - nn * vpr);
+        dn = G / vpr; dcol = G - dn * vpr;
+    }
+    __device__ __forceinline__ bool more() const { return left != 0u; }
+    __device__ __forceinline__ bool next(long long& addr) {
+        const bool ok = left != 0u;
+        addr = base + (long long)n * row_stride + col;
+        left -= ok ? 1u : 0u;
+        col += dcol; n += dn;
+        if (col >= vpr) { col -= vpr; n++; }
+        return ok;
+    }
+};
+
+// Tile geometry shared by all kernels.
+struct TileCtx {
+    long long c, ltile, pidx, u0, u1, base_unit;
+    long long peel_begin0, peel_n0, peel_begin1, peel_n1;   // scalar head / tail (regime 0, VEC > 1, split 0)
+    int j;
+};
+template <int VEC>
+__device__ __forceinline__ TileCtx make_tile(const Seg& sg, long long gtile) {
+    TileCtx t;
+    t.ltile = gtile - sg.tile_begin;
+    t.c = t.ltile / sg.splits;
+    t.j = (int)(t.ltile - t.c * sg.splits);
+    t.pidx = sg.per_channel ? t.c : 0;
+    long long chan_units = sg.chan_units;
+    t.peel_n0 = t.peel_n1 = 0; t.peel_begin0 = t.peel_begin1 = 0;
+    if (sg.regime == 0) {
+        // channel c is the contiguous element range [c*inner, (c+1)*inner); with VEC > 1 only the
+        // 16-byte aligned body is vectorised, head / tail elements are peeled by split 0
+        const long long rb = t.c * sg.inner, re = rb + sg.inner;
+        long long bb = rb, be = re;
+        if (VEC > 1) {
+            bb = (rb + VEC - 1) / VEC * VEC;
+            be = re / VEC * VEC;
+            if (bb > be) { bb = re; be = re; }
+            if (t.j == 0) { t.peel_begin0 = rb; t.peel_n0 = (bb < re ? bb : re) - rb; t.peel_begin1 = be; t.peel_n1 = re - be; }
+        }
+        chan_units = (be - bb) / VEC;
+        t.base_unit = bb / VEC;
+    } else {
+        t.base_unit = t.c * sg.vpr;   // channel c starts vpr units after channel c-1 inside a row group
+    }
+    t.u0 = (long long)t.j * sg.units_per_split;
+    const long long e = t.u0 + sg.units_per_split;
+    t.u1 = e < chan_units ? e : chan_units;
+    if (t.u0 > t.u1) t.u0 = t.u1;
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int VEC, bool INIT, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
+    using Tr = ElemTraits<T>;
+    constexpr int GROUPS = THREADS / G;
+    __shared__ Seg smem_seg[GROUPS];
+    const int grp = threadIdx.x / G, tg = threadIdx.x % G;
+    const long long gtile = (long long)blockIdx.x * GROUPS + grp;
+    if (!stage_segment<G, THREADS>(single, table, nseg, gtile, total_tiles, &smem_seg[grp])) return;
+    const Seg& sg = smem_seg[grp];
+    const TileCtx tl = make_tile<VEC>(sg, gtile);
+    const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    T* __restrict__ yp = reinterpret_cast<T*>(sg.y);
+    const Chan ch = make_chan<MODE>(load_param(sg.scale, tl.pidx, sg.pdt), load_param(sg.shift, tl.pidx, sg.pdt), sg);
+
+    if (VEC > 1) {
+        for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
+            const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
+            yp[e] = INIT ? xp[e] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xp[e]), ch));
+        }
+    }
+    Walker w;
+    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    while (w.more()) {
+        long long addr[UNROLL];
+        bool ok[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
+        if (VEC > 1) {
+            uint4 xr[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                if (ok[k]) xr[k] = ld128<LD>(reinterpret_cast<const uint4*>(xp) + addr[k]);
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                if (!ok[k]) continue;
+                if (INIT) { st128<ST>(reinterpret_cast<uint4*>(yp) + addr[k], xr[k]); continue; }
+                float f[Tr::VEC];
+                Tr::unpack(xr[k], f);
+#pragma unroll
+                for (int e = 0; e < Tr::VEC; e++) f[e] = fq_forward<MODE>(f[e], ch);
+                st128<ST>(reinterpret_cast<uint4*>(yp) + addr[k], Tr::pack(f));
+            }
+        } else {
+            T xr[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                if (ok[k]) xr[k] = xp[addr[k]];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                if (ok[k]) yp[addr[k]] = INIT ? xr[k] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xr[k]), ch));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross-tile finalisation shared by backward and stats: publish this tile's two partial sums,
+// take a ticket, and let the LAST arriver of the channel add all partials of the channel in a
+// fixed order (bit-reproducible whatever the arrival order).  Returns true in every thread of
+// the finishing group, with the channel totals valid in group thread 0.
+// ---------------------------------------------------------------------------------------------
+template <int G, int THREADS>
+__device__ __forceinline__ bool channel_finish(const Seg& sg, const TileCtx& tl, double& a, double& b,
+                                               double* red, int* last_flag, int tg) {
+    group_sum2<G, THREADS>(a, b, red);
+    if (sg.splits == 1) return true;
+    if (tg == 0) {
+        sg.partials[2 * tl.ltile] = a;
+        sg.partials[2 * tl.ltile + 1] = b;
+        __threadfence();
+        const unsigned prev = atomicAdd(&sg.counters[tl.c], 1u);
+        *last_flag = (prev == (unsigned)sg.splits - 1u);
+    }
+    group_sync<G, THREADS>();
+    const bool last = *last_flag != 0;
+    if (!last) return false;
+    __threadfence();
+    a = 0.0; b = 0.0;
+    const double* p = sg.partials + 2 * (tl.c * sg.splits);
+    for (int i = tg; i < sg.splits; i += G) { a += __ldcg(p + 2 * i); b += __ldcg(p + 2 * i + 1); }
+    group_sum2<G, THREADS>(a, b, red);
+    if (tg == 0) sg.counters[tl.c] = 0u;          // leave the workspace zeroed for the next call
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward kernel: gx write + grad_scale / grad_shift reduction; x and grad are read exactly once
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int VEC, int BMODE, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
+    using Tr = ElemTraits<T>;
+    constexpr int GROUPS = THREADS / G;
+    __shared__ Seg smem_seg[GROUPS];
+    __shared__ double red[64];
+    __shared__ int last_flag[GROUPS];
+    const int grp = threadIdx.x / G, tg = threadIdx.x % G;
+    const long long gtile = (long long)blockIdx.x * GROUPS + grp;
+    if (!stage_segment<G, THREADS>(single, table, nseg, gtile, total_tiles, &smem_seg[grp])) return;
+    const Seg& sg = smem_seg[grp];
+    const TileCtx tl = make_tile<VEC>(sg, gtile);
+    const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    const T* __restrict__ gp = reinterpret_cast<const T*>(sg.g);
+    T* __restrict__ gxp = reinterpret_cast<T*>(sg.gx);
+    const bool write_gx = gxp != nullptr;
+    const Chan ch = make_chan<MODE>(load_param(sg.scale, tl.pidx, sg.pdt), load_param(sg.shift, tl.pidx, sg.pdt), sg);
+
+    double accS = 0.0, accB = 0.0;
+    if (VEC > 1) {
+        for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
+            const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
+            float ls = 0.f, lb = 0.f;
+            const float dx = fq_backward<MODE, BMODE>(Tr::to_f(gp[e]), Tr::to_f(xp[e]), ch, ls, lb);
+            if (write_gx) gxp[e] = bmode_passthrough(BMODE) ? gp[e] : Tr::from_f(dx);
+            accS += (double)ls; accB += (double)lb;
+        }
+    }
+    Walker w;
+    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    while (w.more()) {
+        long long addr[UNROLL];
+        bool ok[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
+        float ls = 0.f, lb = 0.f;   // fp32 partial over <= UNROLL*VEC terms, then promoted to double
+        if (VEC > 1) {
+            uint4 xr[UNROLL], gr[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                if (ok[k]) {
+                    xr[k] = ld128<LD>(reinterpret_cast<const uint4*>(xp) + addr[k]);
+                    gr[k] = ld128<LD>(reinterpret_cast<const uint4*>(gp) + addr[k]);
+                }
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                if (!ok[k]) continue;
+                float fx[Tr::VEC], fg[Tr::VEC];
+                Tr::unpack(xr[k], fx);
+                Tr::unpack(gr[k], fg);
+#pragma unroll
+                for (int e = 0; e < Tr::VEC; e++) fg[e] = fq_backward<MODE, BMODE>(fg[e], fx[e], ch, ls, lb);
+                if (write_gx) {
+                    if (bmode_passthrough(BMODE)) st128<ST>(reinterpret_cast<uint4*>(gxp) + addr[k], gr[k]);
+                    else st128<ST>(reinterpret_cast<uint4*>(gxp) + addr[k], Tr::pack(fg));
+                }
+            }
+        } else {
+            T xr[UNROLL], gr[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                if (ok[k]) { xr[k] = xp[addr[k]]; gr[k] = gp[addr[k]]; }
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                if (!ok[k]) continue;
+                const float dx = fq_backward<MODE, BMODE>(Tr::to_f(gr[k]), Tr::to_f(xr[k]), ch, ls, lb);
+                if (write_gx) gxp[addr[k]] = bmode_passthrough(BMODE) ? gr[k] : Tr::from_f(dx);
+            }
+        }
+        accS += (double)ls; accB += (double)lb;
+    }
+
+    if (!bmode_reduces(BMODE)) {   // eval: parameters get exact zeros (lsq_kernel.h:143-144)
+        if (tl.j == 0 && tg == 0) {
+            store_param(sg.gscale, tl.pidx, sg.pdt, 0.0);
+            store_param(sg.gshift, tl.pidx, sg.pdt, 0.0);
+        }
+        return;
+    }
+    if (!channel_finish<G, THREADS>(sg, tl, accS, accB, red, &last_flag[grp], tg)) return;
+    if (tg == 0) {
+        store_param(sg.gscale, tl.pidx, sg.pdt, accS * sg.gs);
+        store_param(sg.gshift, tl.pidx, sg.pdt, sg.sym ? 0.0 : accB * sg.gs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// mu +- 3 sigma weight-init statistics (observers.py:329-337): ONE read of w.
+// Shifted sums in double: S1 = sum(w - p), S2 = sum((w - p)^2), p = first element of the channel.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC, int G, int THREADS, int UNROLL, int LD, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
+    using Tr = ElemTraits<T>;
+    constexpr int GROUPS = THREADS / G;
+    __shared__ Seg smem_seg[GROUPS];
+    __shared__ double red[64];
+    __shared__ int last_flag[GROUPS];
+    const int grp = threadIdx.x / G, tg = threadIdx.x % G;
+    const long long gtile = (long long)blockIdx.x * GROUPS + grp;
+    if (!stage_segment<G, THREADS>(single, table, nseg, gtile, total_tiles, &smem_seg[grp])) return;
+    const Seg& sg = smem_seg[grp];
+    const TileCtx tl = make_tile<VEC>(sg, gtile);
+    const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    const double pivot = (double)Tr::to_f(xp[tl.c * sg.inner]);      // element (0, c, 0)
+
+    double s1 = 0.0, s2 = 0.0;
+    if (VEC > 1) {
+        for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
+            const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
+            const double d = (double)Tr::to_f(xp[e]) - pivot;
+            s1 += d; s2 = fma(d, d, s2);
+        }
+    }
+    Walker w;
+    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    while (w.more()) {
+        long long addr[UNROLL];
+        bool ok[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
+        if (VEC > 1) {
+            uint4 xr[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                if (ok[k]) xr[k] = ld128<LD>(reinterpret_cast<const uint4*>(xp) + addr[k]);
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                if (!ok[k]) continue;
+                float f[Tr::VEC];
+                Tr::unpack(xr[k], f);
+#pragma unroll
+                for (int e = 0; e < Tr::VEC; e++) {
+                    const double d = (double)f[e] - pivot;
+                    s1 += d; s2 = fma(d, d, s2);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                if (!ok[k]) continue;
+                const double d = (double)Tr::to_f(xp[addr[k]]) - pivot;
+                s1 += d; s2 = fma(d, d, s2);
+            }
+        }
+    }
+    if (!channel_finish<G, THREADS>(sg, tl, s1, s2, red, &last_flag[grp], tg)) return;
+    if (tg == 0) {
+        const double K = (double)sg.chan_elems;
+        const double mean = pivot + s1 / K;
+        double var = (s2 - s1 * s1 / K) / (K - 1.0);               // unbiased (torch.std default); K == 1 -> NaN
+        if (var < 0.0) var = 0.0;
+        const float mu = (float)mean, sd = (float)sqrt(var);
+        const float lo = fabsf(__fsub_rn(mu, __fmul_rn(3.0f, sd)));
+        const float hi = fabsf(__fadd_rn(mu, __fmul_rn(3.0f, sd)));
+        sg.stats_out[tl.c] = __fdiv_rn(fmaxf(lo, hi), sg.stats_denom);
+    }
+}
+
+}  // namespace lsqb200

@@ -1,0 +1,145 @@
+// lsq_host.h -- host-side launch planning shared by the C-ABI library and the tuning tool.
+// Pure host code: turns a contiguous (outer, C, inner) tensor into the Seg descriptor the
+// kernels in lsq_device.cuh consume.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+
+#include "lsq_device.cuh"
+
+namespace lsqb200 {
+
+// Compile-time launch shape of the product kernels (tools/tune.cu instantiates alternatives).
+constexpr int kThreads = 256;
+constexpr int kUnrollFwd = 4;
+constexpr int kUnrollBwd = 4;
+constexpr int kUnrollStats = 4;
+constexpr int kMinBlocksFwd = 4;   // __launch_bounds__ min CTAs/SM -> register cap 64
+constexpr int kMinBlocksBwd = 3;   // -> register cap 85
+constexpr int kLd = LD_NC_NOALLOC;   // streaming loads: read-only path, no L1 allocation
+constexpr int kSt = ST_DEFAULT;
+
+using KernelFn = void (*)(const Seg, const Seg*, int, long long);
+// defined in kern_fwd.cu / kern_bwd_*.cu / kern_stats.cu (one translation unit per family so they build in parallel)
+KernelFn get_fwd_kernel(int xdtype, int mode, bool vec, bool init, int group);
+KernelFn get_bwd_kernel_f32(int mode, bool vec, int bmode, int group);
+KernelFn get_bwd_kernel_f16(int mode, bool vec, int bmode, int group);
+KernelFn get_bwd_kernel_bf16(int mode, bool vec, int bmode, int group);
+inline KernelFn get_bwd_kernel(int xdtype, int mode, bool vec, int bmode, int group) {
+    if (xdtype == DT_F32) return get_bwd_kernel_f32(mode, vec, bmode, group);
+    if (xdtype == DT_F16) return get_bwd_kernel_f16(mode, vec, bmode, group);
+    return get_bwd_kernel_bf16(mode, vec, bmode, group);
+}
+KernelFn get_stats_kernel(int xdtype, bool vec, int group);
+
+// Fixed workspace layout (see lsqb200_workspace_bytes): tickets first, partials after.
+constexpr long long kMaxCounters = 4096;     // channels that may be split across tiles
+constexpr long long kMaxSplitTiles = 16384;  // tiles of a split launch (2 doubles each)
+constexpr size_t kWorkspaceBytes = kMaxCounters * 4 + kMaxSplitTiles * 16;
+
+struct Tuning {
+    int sm_count = 148;
+    int tiles_per_sm = 16;      // target tiles (of a big tensor) per SM
+    int max_tile_kb = 0;        // 0 = no cap; else cap tile bytes (more, smaller tiles)
+    int warp_units = 512;       // tiles with <= this many units go to warp groups
+    int min_iters = 2;          // never split below min_iters full group iterations
+};
+
+enum : int { K_FWD = 0, K_BWD = 1, K_STATS = 2 };
+
+struct Geometry {
+    int regime, vec, group, splits;
+    long long outer, C, inner;   // after collapsing C == 1
+    long long vpr, row_stride, chan_units, units_per_split, tiles, grid;
+};
+
+inline int elem_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+inline Geometry plan_geometry(long long outer, long long C, long long inner, int xdtype, int kind,
+                              bool aligned16, const Tuning& tn) {
+    Geometry g{};
+    if (C == 1) { inner *= outer; outer = 1; }      // per-tensor: one contiguous channel
+    g.outer = outer; g.C = C; g.inner = inner;
+    const int es = elem_size(xdtype), vfull = 16 / es;
+    g.regime = (outer == 1) ? 0 : 1;
+    g.vec = vfull;
+    if (!aligned16) g.vec = 1;
+    else if (g.regime == 1 && inner % vfull != 0) g.vec = 1;   // rows would lose 16 B alignment
+    if (g.regime == 0) {
+        g.vpr = 1LL << 30; g.row_stride = 1LL << 30;   // artificial rows: contiguous, 32-bit walker state
+        g.chan_units = (g.vec == 1) ? inner : (inner + g.vec - 1) / g.vec;   // upper bound of the aligned body
+    } else {
+        g.vpr = inner / g.vec; g.row_stride = C * g.vpr;
+        g.chan_units = outer * g.vpr;
+    }
+    const int unroll = kind == K_FWD ? kUnrollFwd : (kind == K_BWD ? kUnrollBwd : kUnrollStats);
+    // how many tiles do we want overall
+    const long long target = (long long)tn.sm_count * tn.tiles_per_sm;
+    long long splits = (target + C - 1) / C;
+    const long long min_units = (long long)kThreads * unroll * tn.min_iters;
+    long long max_splits = g.chan_units / min_units;
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+    if (tn.max_tile_kb > 0) {
+        const long long cap_units = (long long)tn.max_tile_kb * 1024 / ((long long)g.vec * es);
+        const long long s2 = (g.chan_units + cap_units - 1) / cap_units;
+        if (s2 > splits) splits = s2;
+    }
+    if (kind == K_FWD) {
+        // no reduction: nothing limits the split count but launch granularity
+    } else {
+        if (C > kMaxCounters) splits = 1;
+        while (splits > 1 && C * splits > kMaxSplitTiles) splits--;
+    }
+    if (splits < 1) splits = 1;
+    long long ups = (g.chan_units + splits - 1) / splits;
+    if (ups < 1) ups = 1;
+    // whole group iterations per split keep every split's access pattern identical
+    g.group = (ups <= tn.warp_units) ? 32 : kThreads;
+    const long long q = (long long)g.group;
+    ups = (ups + q - 1) / q * q;
+    splits = (g.chan_units + ups - 1) / ups;
+    if (splits < 1) splits = 1;
+    g.units_per_split = ups;
+    g.splits = (int)splits;
+    g.tiles = C * splits;
+    const long long gpc = kThreads / g.group;
+    g.grid = (g.tiles + gpc - 1) / gpc;
+    return g;
+}
+
+struct SegArgs {
+    const void* x; void* y; const void* g; void* gx;
+    const void* scale; const void* shift; void* gscale; void* gshift;
+    float* stats_out;
+    long long outer, C, inner;
+    int xdtype, pdtype, per_channel;
+    long long qmin, qmax, tmin, tmax;
+    double grad_scaler;
+    int use_grad_scaling, sym;
+};
+
+inline bool is_aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline Seg make_seg(const SegArgs& a, const Geometry& g, double* partials, unsigned* counters, long long tile_begin) {
+    Seg s;
+    std::memset(&s, 0, sizeof(s));
+    s.x = a.x; s.y = a.y; s.g = a.g; s.gx = a.gx;
+    s.scale = a.scale; s.shift = a.shift; s.gscale = a.gscale; s.gshift = a.gshift;
+    s.partials = partials; s.counters = counters; s.stats_out = a.stats_out;
+    s.C = g.C; s.vpr = g.vpr; s.row_stride = g.row_stride; s.chan_stride = g.vpr;
+    s.inner = g.inner; s.chan_units = g.chan_units; s.units_per_split = g.units_per_split;
+    s.tile_begin = tile_begin; s.chan_elems = g.outer * g.inner;
+    const double numel = (double)a.outer * (double)a.C * (double)a.inner;
+    s.gs = a.use_grad_scaling ? a.grad_scaler / std::sqrt(numel * (double)a.qmax) : a.grad_scaler;
+    s.qmin = (float)a.qmin; s.qmax = (float)a.qmax; s.tmin = (float)a.tmin; s.tmax = (float)a.tmax;
+    // bitness = ceil(log(qmax - qmin) / log 2) - 1   (observers.py:333)
+    const int bitness = (int)std::ceil(std::log((double)(a.qmax - a.qmin)) / std::log(2.0)) - 1;
+    s.stats_denom = (float)std::ldexp(1.0, bitness);
+    s.splits = g.splits; s.regime = g.regime; s.per_channel = a.per_channel; s.pdt = a.pdtype;
+    s.sym = a.sym; s.vec = g.vec;
+    return s;
+}
+
+}  // namespace lsqb200
