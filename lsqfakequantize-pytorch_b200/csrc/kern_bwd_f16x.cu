@@ -1,4 +1,4 @@
-// kern_bwd_bf16.cu -- instantiations of the backward kernel family (bf16 tensors).
+// kern_bwd_f16x.cu -- instantiations of the backward kernel family (fp16 tensors with fp16 parameters, c10::Half-exact).
 #include "lsq_host.h"
 namespace lsqb200 {
 namespace {
@@ -27,8 +27,8 @@ KernelFn pick(int nw, int bmode, int group) {
     }
 }
 }  // namespace
-KernelFn get_bwd_kernel_bf16(int mode, int nw, int bmode, int group) {
+KernelFn get_bwd_kernel_f16_exact(int mode, int nw, int bmode, int group) {
     (void)mode;
-    return pick<__nv_bfloat16, M_FP32>(nw, bmode, group);
+    return pick<__half, M_HALF_EXACT>(nw, bmode, group);
 }
 }  // namespace lsqb200

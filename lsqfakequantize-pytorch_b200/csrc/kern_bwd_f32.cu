@@ -2,9 +2,9 @@
 #include "lsq_host.h"
 namespace lsqb200 {
 namespace {
-template <typename T, int MODE, int VEC_, int G_>
+template <typename T, int MODE, int NW, int G_>
 KernelFn pick_b(int bmode) {
-#define LSQ_B(B_) lsq_bwd_kernel<T, MODE, VEC_, B_, G_, kThreads, kUnrollBwd, kLd, kSt, kMinBlocksBwd>
+#define LSQ_B(B_) lsq_bwd_kernel<T, MODE, NW, B_, G_, kThreads, unroll_for(kUnrollBwd, NW), kLd, kSt, kMinBlocksBwd>
     switch (bmode) {
         case B_NORMAL: return LSQ_B(B_NORMAL);
         case B_INIT: return LSQ_B(B_INIT);
@@ -13,15 +13,22 @@ KernelFn pick_b(int bmode) {
     }
 #undef LSQ_B
 }
+template <typename T, int MODE, int NW>
+KernelFn pick_g(int bmode, int group) {
+    return group == 32 ? pick_b<T, MODE, NW, 32>(bmode) : pick_b<T, MODE, NW, kThreads>(bmode);
+}
 template <typename T, int MODE>
-KernelFn pick(bool vec, int bmode, int group) {
-    constexpr int V = ElemTraits<T>::VEC;
-    if (group == 32) return vec ? pick_b<T, MODE, V, 32>(bmode) : pick_b<T, MODE, 1, 32>(bmode);
-    return vec ? pick_b<T, MODE, V, kThreads>(bmode) : pick_b<T, MODE, 1, kThreads>(bmode);
+KernelFn pick(int nw, int bmode, int group) {
+    switch (nw) {
+        case 8: return pick_g<T, MODE, 8>(bmode, group);
+        case 4: return pick_g<T, MODE, 4>(bmode, group);
+        case 2: return pick_g<T, MODE, 2>(bmode, group);
+        default: return pick_g<T, MODE, 0>(bmode, group);
+    }
 }
 }  // namespace
-KernelFn get_bwd_kernel_f32(int mode, bool vec, int bmode, int group) {
+KernelFn get_bwd_kernel_f32(int mode, int nw, int bmode, int group) {
     (void)mode;
-    return pick<float, M_FP32>(vec, bmode, group);
+    return pick<float, M_FP32>(nw, bmode, group);
 }
 }  // namespace lsqb200

@@ -55,6 +55,7 @@ int pick_mode(int xdt, int pdt) {
 
 int check_q(const lsqb200_qargs* q) {
     if (!q) return fail(LSQB200_ERR_ARG, "qargs is NULL");
+    if (q->quant_min >= q->quant_max) return fail(LSQB200_ERR_ARG, "quant_min must be smaller than quant_max");
     return 0;
 }
 
@@ -97,11 +98,10 @@ int forward_common(const void* x, void* y, const void* scale, const void* shift,
     if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
     if (outer * C * inner == 0) return 0;
     if (!x || !y || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
-    const bool al = is_aligned16(x) && is_aligned16(y);
-    const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, al, tuning());
+    const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, common_alignment({x, y}), tuning());
     SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
     const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
-    KernelFn k = get_fwd_kernel(xdt, mode, g.vec > 1, q->init_mode != 0, g.group);
+    KernelFn k = get_fwd_kernel(xdt, mode, g.nw, q->init_mode != 0, g.group);
     return launch(k, seg, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
@@ -125,19 +125,18 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
         return 0;
     }
     if (!grad || !x || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
-    const bool al = is_aligned16(x) && is_aligned16(grad) && is_aligned16(gx);
-    const Geometry g = plan_geometry(outer, C, inner, xdt, K_BWD, al, tuning());
+    const Geometry g = plan_geometry(outer, C, inner, xdt, K_BWD, common_alignment({x, grad, gx}), tuning());
     double* partials = nullptr;
     unsigned* counters = nullptr;
     if (g.splits > 1) {
-        if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u))
+        if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
             return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
         counters = reinterpret_cast<unsigned*>(workspace);
         partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kMaxCounters * 4);
     }
     SegArgs a = seg_args(x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, xdt, pdt, per_channel, q);
     const Seg seg = make_seg(a, g, partials, counters, 0);
-    KernelFn k = get_bwd_kernel(xdt, mode, g.vec > 1, bmode_of(q), g.group);
+    KernelFn k = get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
     return launch(k, seg, nullptr, 0, g.tiles, g.grid, st);
 }
 
@@ -175,16 +174,16 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         const int mode = pick_mode(s.xdtype, s.pdtype);
         if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair in plan");
         if (s.outer * s.C * s.inner == 0) continue;
-        bool al = is_aligned16(s.x);
-        if (kind == K_FWD) al = al && is_aligned16(s.y);
-        if (kind == K_BWD) al = al && is_aligned16(s.grad) && is_aligned16(s.gx);
+        int al = common_alignment({s.x});
+        if (kind == K_FWD) al = common_alignment({s.x, s.y});
+        if (kind == K_BWD) al = common_alignment({s.x, s.grad, s.gx});
         Geometry g = plan_geometry(s.outer, s.C, s.inner, s.xdtype, kind, al, tn);
         int variant = 0;
         KernelFn k = nullptr;
-        if (kind == K_FWD) { variant = s.q.init_mode != 0; k = get_fwd_kernel(s.xdtype, mode, g.vec > 1, variant, g.group); }
-        else if (kind == K_BWD) { variant = bmode_of(&s.q); k = get_bwd_kernel(s.xdtype, mode, g.vec > 1, variant, g.group); }
-        else { k = get_stats_kernel(s.xdtype, g.vec > 1, g.group); }
-        const ClassKey key{s.xdtype, kind == K_STATS ? 0 : mode, g.vec > 1, variant, g.group};
+        if (kind == K_FWD) { variant = s.q.init_mode != 0; k = get_fwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
+        else if (kind == K_BWD) { variant = bmode_of(&s.q); k = get_bwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
+        else { k = get_stats_kernel(s.xdtype, g.nw, g.group); }
+        const ClassKey key{s.xdtype, kind == K_STATS ? 0 : mode, g.nw, variant, g.group};
         auto it = index.find(key);
         if (it == index.end()) {
             it = index.emplace(key, out.size()).first;
@@ -267,6 +266,8 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "warp_units") g_tuning.warp_units = v;
         else if (k == "min_iters") g_tuning.min_iters = v;
         else if (k == "sm_count") g_tuning.sm_count = v;
+        else if (k == "max_unit_bytes") g_tuning.max_unit_bytes = v;
+        else if (k == "interleave") g_tuning.interleave = v;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;
     }
@@ -281,7 +282,7 @@ int lsqb200_set_tuning(const char* spec) {
 int lsqb200_query_launch(int64_t outer, int64_t C, int64_t inner, int xdtype, int backward, int aligned16,
                          lsqb200_launch_info* out) {
     if (!out || outer < 0 || C < 0 || inner < 0 || xdtype < 0 || xdtype > 2) return fail(LSQB200_ERR_ARG, "bad argument");
-    const Geometry g = plan_geometry(outer, C, inner, xdtype, backward ? K_BWD : K_FWD, aligned16 != 0, tuning());
+    const Geometry g = plan_geometry(outer, C, inner, xdtype, backward ? K_BWD : K_FWD, aligned16 ? 32 : 2, tuning());
     out->regime = g.regime; out->vec = g.vec; out->threads = kThreads; out->splits = g.splits;
     out->grid = g.grid; out->units_per_split = g.units_per_split;
     return 0;
@@ -319,11 +320,11 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
     if (quant_max <= quant_min) return fail(LSQB200_ERR_ARG, "quant_max must exceed quant_min");
     if (outer * C * inner == 0) return 0;
     if (!w || !scale_out) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
-    const Geometry g = plan_geometry(outer, C, inner, xdtype, K_STATS, is_aligned16(w), tuning());
+    const Geometry g = plan_geometry(outer, C, inner, xdtype, K_STATS, common_alignment({w}), tuning());
     double* partials = nullptr;
     unsigned* counters = nullptr;
     if (g.splits > 1) {
-        if (!workspace || workspace_bytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u))
+        if (!workspace || workspace_bytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
             return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
         counters = reinterpret_cast<unsigned*>(workspace);
         partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kMaxCounters * 4);
@@ -334,7 +335,7 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
                          C > 1, &q);
     a.stats_out = scale_out;
     const Seg seg = make_seg(a, g, partials, counters, 0);
-    KernelFn k = get_stats_kernel(xdtype, g.vec > 1, g.group);
+    KernelFn k = get_stats_kernel(xdtype, g.nw, g.group);
     return launch(k, seg, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 

@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace lsqb200 {
 
 enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
@@ -66,7 +68,9 @@ struct Seg {
     int per_channel;
     int pdt;
     int sym;
-    int vec;               // elements per unit actually used (1 or 16/sizeof(T))
+    int vec;               // elements per unit actually used
+    int interleave;        // 1: splits of a channel are interleaved at group granularity
+    int group;             // threads per tile-owning group (32 or THREADS)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -75,28 +79,55 @@ struct Seg {
 enum : int { LD_DEFAULT = 0, LD_NC_NOALLOC = 1, LD_EVICT_FIRST = 2 };
 enum : int { ST_DEFAULT = 0, ST_CS = 1, ST_NOALLOC = 2 };
 
-template <int LD>
-__device__ __forceinline__ uint4 ld128(const void* p) {
-    uint4 r;
-    if (LD == LD_NC_NOALLOC)
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else if (LD == LD_EVICT_FIRST)
-        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else
-        asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+// A unit is NW 32-bit words moved by ONE instruction: NW = 8 -> LDG.E.256 / STG.E.256 (new on
+// sm_100), 4 -> 128-bit, 2 -> 64-bit.  NW = 0 denotes the scalar (element-at-a-time) path.
+template <int NW> struct Raw { uint32_t w[NW == 0 ? 1 : NW]; };
+
+template <int LD, int NW>
+__device__ __forceinline__ Raw<NW> ld_unit(const void* p) {
+    Raw<NW> r;
+    if (NW == 8) {
+        if (LD == LD_EVICT_FIRST)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4 % NW]), "=r"(r.w[5 % NW]), "=r"(r.w[6 % NW]), "=r"(r.w[7 % NW]) : "l"(p));
+        else if (LD == LD_NC_NOALLOC)
+            asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4 % NW]), "=r"(r.w[5 % NW]), "=r"(r.w[6 % NW]), "=r"(r.w[7 % NW]) : "l"(p));
+        else
+            asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4 % NW]), "=r"(r.w[5 % NW]), "=r"(r.w[6 % NW]), "=r"(r.w[7 % NW]) : "l"(p));
+    } else if (NW == 4) {
+        if (LD == LD_DEFAULT)
+            asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1 % NW]), "=r"(r.w[2 % NW]), "=r"(r.w[3 % NW]) : "l"(p));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1 % NW]), "=r"(r.w[2 % NW]), "=r"(r.w[3 % NW]) : "l"(p));
+    } else {
+        if (LD == LD_DEFAULT)
+            asm volatile("ld.global.v2.u32 {%0,%1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1 % NW]) : "l"(p));
+        else
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1 % NW]) : "l"(p));
+    }
     return r;
 }
-template <int ST>
-__device__ __forceinline__ void st128(void* p, const uint4& v) {
-    if (ST == ST_CS)
-        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else if (ST == ST_NOALLOC)
-        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-    else
-        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+template <int ST, int NW>
+__device__ __forceinline__ void st_unit(void* p, const Raw<NW>& v) {
+    if (NW == 8) {
+        if (ST == ST_CS)
+            asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4 % NW]), "r"(v.w[5 % NW]), "r"(v.w[6 % NW]), "r"(v.w[7 % NW]) : "memory");
+        else if (ST == ST_NOALLOC)
+            asm volatile("st.global.L1::no_allocate.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4 % NW]), "r"(v.w[5 % NW]), "r"(v.w[6 % NW]), "r"(v.w[7 % NW]) : "memory");
+        else
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4 % NW]), "r"(v.w[5 % NW]), "r"(v.w[6 % NW]), "r"(v.w[7 % NW]) : "memory");
+    } else if (NW == 4) {
+        if (ST == ST_CS)
+            asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1 % NW]), "r"(v.w[2 % NW]), "r"(v.w[3 % NW]) : "memory");
+        else if (ST == ST_NOALLOC)
+            asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1 % NW]), "r"(v.w[2 % NW]), "r"(v.w[3 % NW]) : "memory");
+        else
+            asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1 % NW]), "r"(v.w[2 % NW]), "r"(v.w[3 % NW]) : "memory");
+    } else {
+        asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1 % NW]) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -104,62 +135,51 @@ __device__ __forceinline__ void st128(void* p, const uint4& v) {
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct ElemTraits;
 template <> struct ElemTraits<float> {
-    static constexpr int VEC = 4;
+    static constexpr int PER_WORD = 1;
     static __device__ __forceinline__ float to_f(float v) { return v; }
     static __device__ __forceinline__ float from_f(float v) { return v; }
-    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[4]) {
-        f[0] = __uint_as_float(r.x); f[1] = __uint_as_float(r.y);
-        f[2] = __uint_as_float(r.z); f[3] = __uint_as_float(r.w);
-    }
-    static __device__ __forceinline__ uint4 pack(const float (&f)[4]) {
-        return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
-    }
+    static __device__ __forceinline__ void unpack_word(uint32_t w, float* f) { f[0] = __uint_as_float(w); }
+    static __device__ __forceinline__ uint32_t pack_word(const float* f) { return __float_as_uint(f[0]); }
 };
 template <> struct ElemTraits<__half> {
-    static constexpr int VEC = 8;
+    static constexpr int PER_WORD = 2;
     static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
     static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
-    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
-            float2 t = __half22float2(h);
-            f[2 * i] = t.x; f[2 * i + 1] = t.y;
-        }
+    static __device__ __forceinline__ void unpack_word(uint32_t w, float* f) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        f[0] = t.x; f[1] = t.y;
     }
-    static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        return make_uint4(w[0], w[1], w[2], w[3]);
+    static __device__ __forceinline__ uint32_t pack_word(const float* f) {
+        const __half2 h = __floats2half2_rn(f[0], f[1]);
+        return *reinterpret_cast<const uint32_t*>(&h);
     }
 };
 template <> struct ElemTraits<__nv_bfloat16> {
-    static constexpr int VEC = 8;
+    static constexpr int PER_WORD = 2;
     static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
     static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
-    static __device__ __forceinline__ void unpack(const uint4& r, float (&f)[8]) {
-        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            f[2 * i] = __uint_as_float(w[i] << 16);
-            f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-        }
+    static __device__ __forceinline__ void unpack_word(uint32_t w, float* f) {
+        f[0] = __uint_as_float(w << 16); f[1] = __uint_as_float(w & 0xffff0000u);
     }
-    static __device__ __forceinline__ uint4 pack(const float (&f)[8]) {
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        return make_uint4(w[0], w[1], w[2], w[3]);
+    static __device__ __forceinline__ uint32_t pack_word(const float* f) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
+        return *reinterpret_cast<const uint32_t*>(&h);
     }
 };
+// elements per unit
+template <typename T, int NW> struct UnitOf { static constexpr int VEC = NW == 0 ? 1 : NW * ElemTraits<T>::PER_WORD; };
+template <typename T, int NW>
+__device__ __forceinline__ void unpack_unit(const Raw<NW>& r, float* f) {
+#pragma unroll
+    for (int i = 0; i < NW; i++) ElemTraits<T>::unpack_word(r.w[i], f + i * ElemTraits<T>::PER_WORD);
+}
+template <typename T, int NW>
+__device__ __forceinline__ Raw<NW> pack_unit(const float* f) {
+    Raw<NW> r;
+#pragma unroll
+    for (int i = 0; i < NW; i++) r.w[i] = ElemTraits<T>::pack_word(f + i * ElemTraits<T>::PER_WORD);
+    return r;
+}
 
 __device__ __forceinline__ float load_param(const void* p, long long i, int pdt) {
     if (pdt == DT_F32) return reinterpret_cast<const float*>(p)[i];
@@ -220,26 +240,41 @@ __device__ __forceinline__ float fq_forward(float x, const Chan& c) {
     return __fmul_rn(__fsub_rn(r, c.zp), c.s);
 }
 
-// returns dX (as float); accumulates the two fp32 terms (not yet multiplied by gs)
-template <int MODE, int BMODE>
-__device__ __forceinline__ float fq_backward(float g, float x, const Chan& c, float& accS, float& accB) {
+// returns dX (as float); accumulates the two parameter-gradient terms (not yet multiplied by gs).
+//
+// Same values as lsq_kernel.h:33-61,85-86 with fewer instructions (the bf16 / fp16 backward is
+// issue-bound, not memory-bound, at 6 bytes per element):
+//   * mask = (qmin < xq) && (xq < qmax) is tested on the un-clamped v: identical for
+//     qmin < qmax (checked on the host), including NaN (both false);
+//   * the border factor (xq <= qmin ? qmin - zp : qmax - zp) IS r - zp, because outside the
+//     open range the clamped, rounded r equals qmin or qmax exactly (NaN -> qmax, as in the
+//     reference where fmin drops the NaN first);
+//   * interior term g'*(xfq - x)*inv_s is formed as g' * ((xfq - x)*inv_s) and fused into the
+//     accumulation (<= 2 ulp per term from the reference's left-to-right product; only sums
+//     are observable and they are held to 1e-6);
+//   * dB = (!mask) * g' is exact, so fma(g', 1 - m, acc) adds exactly the reference's term.
+// ACC is float for the streaming kernels (<= UNROLL*VEC terms per partial, then promoted to
+// double) and double for the warp-group kernels that own short channels.
+template <int MODE, int BMODE, typename ACC>
+__device__ __forceinline__ float fq_backward(float g, float x, const Chan& c, ACC& accS, ACC& accB) {
     const float v = affine_v<MODE>(x, c);
-    const float xq = fmaxf(fminf(v, c.qmax), c.qmin);             // min first: NaN -> qmax
-    const bool lt_hi = xq < c.qmax;
-    const bool mask = (c.qmin < xq) && lt_hi;
+    const bool mask = (v > c.qmin) && (v < c.qmax);
     const float m = mask ? 1.0f : 0.0f;
     const float dX = bmode_passthrough(BMODE) ? g : __fmul_rn(g, m);   // g*mask keeps -0 / NaN like the reference
     if (bmode_reduces(BMODE)) {
-        const float r = rintf(xq);
-        const float t = __fsub_rn(r, c.zp);
+        const float xq = fmaxf(fminf(v, c.qmax), c.qmin);          // min first: NaN -> qmax
+        const float t = __fsub_rn(rintf(xq), c.zp);
         const float d = __fmaf_rn(t, c.s, -x);                     // xfq - x, fused as in the reference build
         const float gg = (BMODE == B_INIT) ? __fmul_rn(2.0f, d) : g;
-        const float border = __fmul_rn(gg, (xq <= c.qmin) ? c.c_lo : c.c_hi);
-        const float inner = __fmul_rn(__fmul_rn(gg, d), c.inv_s);
-        const float dS = mask ? inner : border;
-        const float dB = __fmul_rn(__fsub_rn(1.0f, m), gg);        // (!mask) * g'
-        accS = __fadd_rn(accS, dS);
-        accB = __fadd_rn(accB, dB);
+        const float w = mask ? __fmul_rn(d, c.inv_s) : t;
+        const float nm = __fsub_rn(1.0f, m);
+        if (sizeof(ACC) == 4) {
+            accS = __fmaf_rn(gg, w, accS);
+            accB = __fmaf_rn(gg, nm, accB);
+        } else {
+            accS += (ACC)__fmul_rn(gg, w);
+            accB += (ACC)__fmul_rn(gg, nm);
+        }
     }
     return dX;
 }
@@ -309,14 +344,18 @@ struct Walker {
     long long base, row_stride;
     int n, col, dn, dcol, vpr;
     unsigned left;            // units this thread still has to visit, in steps of G (tile-local)
+    // contiguous tiles: this group walks [u0, u1) in steps of G.  Interleaved tiles
+    // (sg.interleave): split j of a channel starts at unit j*G and steps by splits*G, so at any
+    // moment all CTAs of a launch stream through one narrow window of memory.
     template <int G>
     __device__ __forceinline__ void init(const Seg& sg, long long u0, long long u1, long long base_unit, int tg) {
         vpr = (int)sg.vpr; row_stride = sg.row_stride; base = base_unit;
         const long long u = u0 + tg;
-        left = (u < u1) ? (unsigned)((u1 - u + G - 1) / G) : 0u;
+        const long long step = sg.interleave ? (long long)sg.splits * G : (long long)G;
+        left = (u < u1) ? (unsigned)((u1 - u + step - 1) / step) : 0u;
         const long long nn = u / vpr;
         n = (int)nn; col = (int)(u - nn * vpr);
-        dn = G / vpr; dcol = G - dn * vpr;
+        dn = (int)(step / vpr); dcol = (int)(step - (long long)dn * vpr);
     }
     __device__ __forceinline__ bool more() const { return left != 0u; }
     __device__ __forceinline__ bool next(long long& addr) {
@@ -349,7 +388,7 @@ __device__ __forceinline__ TileCtx make_tile(const Seg& sg, long long gtile) {
         // 16-byte aligned body is vectorised, head / tail elements are peeled by split 0
         const long long rb = t.c * sg.inner, re = rb + sg.inner;
         long long bb = rb, be = re;
-        if (VEC > 1) {
+        if constexpr (VEC > 1) {
             bb = (rb + VEC - 1) / VEC * VEC;
             be = re / VEC * VEC;
             if (bb > be) { bb = re; be = re; }
@@ -360,9 +399,14 @@ __device__ __forceinline__ TileCtx make_tile(const Seg& sg, long long gtile) {
     } else {
         t.base_unit = t.c * sg.vpr;   // channel c starts vpr units after channel c-1 inside a row group
     }
-    t.u0 = (long long)t.j * sg.units_per_split;
-    const long long e = t.u0 + sg.units_per_split;
-    t.u1 = e < chan_units ? e : chan_units;
+    if (sg.interleave) {
+        t.u0 = (long long)t.j * sg.group;          // first unit of this split; Walker strides by splits * G
+        t.u1 = chan_units;
+    } else {
+        t.u0 = (long long)t.j * sg.units_per_split;
+        const long long e = t.u0 + sg.units_per_split;
+        t.u1 = e < chan_units ? e : chan_units;
+    }
     if (t.u0 > t.u1) t.u0 = t.u1;
     return t;
 }
@@ -370,10 +414,12 @@ __device__ __forceinline__ TileCtx make_tile(const Seg& sg, long long gtile) {
 // ---------------------------------------------------------------------------------------------
 // forward kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int MODE, int VEC, bool INIT, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
+template <typename T, int MODE, int NW, bool INIT, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
 lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
     using Tr = ElemTraits<T>;
+    constexpr int VEC = UnitOf<T, NW>::VEC;
+    constexpr int UB = NW * 4;   // unit bytes
     constexpr int GROUPS = THREADS / G;
     __shared__ Seg smem_seg[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
@@ -385,7 +431,7 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     T* __restrict__ yp = reinterpret_cast<T*>(sg.y);
     const Chan ch = make_chan<MODE>(load_param(sg.scale, tl.pidx, sg.pdt), load_param(sg.shift, tl.pidx, sg.pdt), sg);
 
-    if (VEC > 1) {
+    if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
             yp[e] = INIT ? xp[e] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xp[e]), ch));
@@ -398,20 +444,20 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
         bool ok[UNROLL];
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
-        if (VEC > 1) {
-            uint4 xr[UNROLL];
+        if constexpr (VEC > 1) {
+            Raw<NW> xr[UNROLL];
 #pragma unroll
-            for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) xr[k] = ld128<LD>(reinterpret_cast<const uint4*>(xp) + addr[k]);
+            for (int k = 0; k < UNROLL; k++)   // tail lanes re-read unit 0 (always valid) so loads stay unconditional
+                xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + (ok[k] ? addr[k] : addr[0]) * UB);
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
-                if (INIT) { st128<ST>(reinterpret_cast<uint4*>(yp) + addr[k], xr[k]); continue; }
-                float f[Tr::VEC];
-                Tr::unpack(xr[k], f);
+                if (INIT) { st_unit<ST, NW>(reinterpret_cast<char*>(yp) + addr[k] * UB, xr[k]); continue; }
+                float f[VEC];
+                unpack_unit<T, NW>(xr[k], f);
 #pragma unroll
-                for (int e = 0; e < Tr::VEC; e++) f[e] = fq_forward<MODE>(f[e], ch);
-                st128<ST>(reinterpret_cast<uint4*>(yp) + addr[k], Tr::pack(f));
+                for (int e = 0; e < VEC; e++) f[e] = fq_forward<MODE>(f[e], ch);
+                st_unit<ST, NW>(reinterpret_cast<char*>(yp) + addr[k] * UB, pack_unit<T, NW>(f));
             }
         } else {
             T xr[UNROLL];
@@ -458,10 +504,12 @@ __device__ __forceinline__ bool channel_finish(const Seg& sg, const TileCtx& tl,
 // ---------------------------------------------------------------------------------------------
 // backward kernel: gx write + grad_scale / grad_shift reduction; x and grad are read exactly once
 // ---------------------------------------------------------------------------------------------
-template <typename T, int MODE, int VEC, int BMODE, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
+template <typename T, int MODE, int NW, int BMODE, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
 lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
     using Tr = ElemTraits<T>;
+    constexpr int VEC = UnitOf<T, NW>::VEC;
+    constexpr int UB = NW * 4;   // unit bytes
     constexpr int GROUPS = THREADS / G;
     __shared__ Seg smem_seg[GROUPS];
     __shared__ double red[64];
@@ -478,13 +526,11 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const Chan ch = make_chan<MODE>(load_param(sg.scale, tl.pidx, sg.pdt), load_param(sg.shift, tl.pidx, sg.pdt), sg);
 
     double accS = 0.0, accB = 0.0;
-    if (VEC > 1) {
+    if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
-            float ls = 0.f, lb = 0.f;
-            const float dx = fq_backward<MODE, BMODE>(Tr::to_f(gp[e]), Tr::to_f(xp[e]), ch, ls, lb);
+            const float dx = fq_backward<MODE, BMODE>(Tr::to_f(gp[e]), Tr::to_f(xp[e]), ch, accS, accB);
             if (write_gx) gxp[e] = bmode_passthrough(BMODE) ? gp[e] : Tr::from_f(dx);
-            accS += (double)ls; accB += (double)lb;
         }
     }
     Walker w;
@@ -494,26 +540,29 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
         bool ok[UNROLL];
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
-        float ls = 0.f, lb = 0.f;   // fp32 partial over <= UNROLL*VEC terms, then promoted to double
-        if (VEC > 1) {
-            uint4 xr[UNROLL], gr[UNROLL];
+        // streaming (CTA-group) kernels: fp32 partial over <= UNROLL*VEC terms, then promoted to
+        // double; warp-group kernels (short channels, cancellation-prone sums): double per term
+        using Acc = typename std::conditional<G == 32, double, float>::type;
+        Acc ls = 0, lb = 0;
+        if constexpr (VEC > 1) {
+            Raw<NW> xr[UNROLL], gr[UNROLL];
 #pragma unroll
-            for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) {
-                    xr[k] = ld128<LD>(reinterpret_cast<const uint4*>(xp) + addr[k]);
-                    gr[k] = ld128<LD>(reinterpret_cast<const uint4*>(gp) + addr[k]);
-                }
+            for (int k = 0; k < UNROLL; k++) {   // tail lanes re-read unit 0 (always valid) so loads stay unconditional
+                const long long a = ok[k] ? addr[k] : addr[0];
+                xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + a * UB);
+                gr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(gp) + a * UB);
+            }
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
-                float fx[Tr::VEC], fg[Tr::VEC];
-                Tr::unpack(xr[k], fx);
-                Tr::unpack(gr[k], fg);
+                float fx[VEC], fg[VEC];
+                unpack_unit<T, NW>(xr[k], fx);
+                unpack_unit<T, NW>(gr[k], fg);
 #pragma unroll
-                for (int e = 0; e < Tr::VEC; e++) fg[e] = fq_backward<MODE, BMODE>(fg[e], fx[e], ch, ls, lb);
+                for (int e = 0; e < VEC; e++) fg[e] = fq_backward<MODE, BMODE>(fg[e], fx[e], ch, ls, lb);
                 if (write_gx) {
-                    if (bmode_passthrough(BMODE)) st128<ST>(reinterpret_cast<uint4*>(gxp) + addr[k], gr[k]);
-                    else st128<ST>(reinterpret_cast<uint4*>(gxp) + addr[k], Tr::pack(fg));
+                    if (bmode_passthrough(BMODE)) st_unit<ST, NW>(reinterpret_cast<char*>(gxp) + addr[k] * UB, gr[k]);
+                    else st_unit<ST, NW>(reinterpret_cast<char*>(gxp) + addr[k] * UB, pack_unit<T, NW>(fg));
                 }
             }
         } else {
@@ -549,10 +598,12 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
 // mu +- 3 sigma weight-init statistics (observers.py:329-337): ONE read of w.
 // Shifted sums in double: S1 = sum(w - p), S2 = sum((w - p)^2), p = first element of the channel.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC, int G, int THREADS, int UNROLL, int LD, int MINB = 1>
+template <typename T, int NW, int G, int THREADS, int UNROLL, int LD, int MINB = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
 lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
     using Tr = ElemTraits<T>;
+    constexpr int VEC = UnitOf<T, NW>::VEC;
+    constexpr int UB = NW * 4;   // unit bytes
     constexpr int GROUPS = THREADS / G;
     __shared__ Seg smem_seg[GROUPS];
     __shared__ double red[64];
@@ -566,7 +617,7 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
     const double pivot = (double)Tr::to_f(xp[tl.c * sg.inner]);      // element (0, c, 0)
 
     double s1 = 0.0, s2 = 0.0;
-    if (VEC > 1) {
+    if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
             const double d = (double)Tr::to_f(xp[e]) - pivot;
@@ -580,18 +631,18 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
         bool ok[UNROLL];
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
-        if (VEC > 1) {
-            uint4 xr[UNROLL];
+        if constexpr (VEC > 1) {
+            Raw<NW> xr[UNROLL];
 #pragma unroll
             for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) xr[k] = ld128<LD>(reinterpret_cast<const uint4*>(xp) + addr[k]);
+                if (ok[k]) xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + addr[k] * UB);
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
-                float f[Tr::VEC];
-                Tr::unpack(xr[k], f);
+                float f[VEC];
+                unpack_unit<T, NW>(xr[k], f);
 #pragma unroll
-                for (int e = 0; e < Tr::VEC; e++) {
+                for (int e = 0; e < VEC; e++) {
                     const double d = (double)f[e] - pivot;
                     s1 += d; s2 = fma(d, d, s2);
                 }

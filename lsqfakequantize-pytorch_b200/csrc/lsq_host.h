@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <initializer_list>
 
 #include "lsq_device.cuh"
 
@@ -15,6 +16,9 @@ constexpr int kThreads = 256;
 constexpr int kUnrollFwd = 4;
 constexpr int kUnrollBwd = 4;
 constexpr int kUnrollStats = 4;
+// units in flight per thread and operand: keep ~64 bytes per operand whatever the unit width
+constexpr int unroll_for(int base, int nw) { return nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base; }
+constexpr int kMinBlocksStats = 2;
 constexpr int kMinBlocksFwd = 4;   // __launch_bounds__ min CTAs/SM -> register cap 64
 constexpr int kMinBlocksBwd = 3;   // -> register cap 85
 constexpr int kLd = LD_NC_NOALLOC;   // streaming loads: read-only path, no L1 allocation
@@ -22,16 +26,18 @@ constexpr int kSt = ST_DEFAULT;
 
 using KernelFn = void (*)(const Seg, const Seg*, int, long long);
 // defined in kern_fwd.cu / kern_bwd_*.cu / kern_stats.cu (one translation unit per family so they build in parallel)
-KernelFn get_fwd_kernel(int xdtype, int mode, bool vec, bool init, int group);
-KernelFn get_bwd_kernel_f32(int mode, bool vec, int bmode, int group);
-KernelFn get_bwd_kernel_f16(int mode, bool vec, int bmode, int group);
-KernelFn get_bwd_kernel_bf16(int mode, bool vec, int bmode, int group);
-inline KernelFn get_bwd_kernel(int xdtype, int mode, bool vec, int bmode, int group) {
-    if (xdtype == DT_F32) return get_bwd_kernel_f32(mode, vec, bmode, group);
-    if (xdtype == DT_F16) return get_bwd_kernel_f16(mode, vec, bmode, group);
-    return get_bwd_kernel_bf16(mode, vec, bmode, group);
+KernelFn get_fwd_kernel(int xdtype, int mode, int nw, bool init, int group);
+KernelFn get_bwd_kernel_f32(int mode, int nw, int bmode, int group);
+KernelFn get_bwd_kernel_f16_mixed(int mode, int nw, int bmode, int group);
+KernelFn get_bwd_kernel_f16_exact(int mode, int nw, int bmode, int group);
+KernelFn get_bwd_kernel_bf16(int mode, int nw, int bmode, int group);
+inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int group) {
+    if (xdtype == DT_F32) return get_bwd_kernel_f32(mode, nw, bmode, group);
+    if (xdtype == DT_F16) return mode == M_HALF_EXACT ? get_bwd_kernel_f16_exact(mode, nw, bmode, group)
+                                                      : get_bwd_kernel_f16_mixed(mode, nw, bmode, group);
+    return get_bwd_kernel_bf16(mode, nw, bmode, group);
 }
-KernelFn get_stats_kernel(int xdtype, bool vec, int group);
+KernelFn get_stats_kernel(int xdtype, int nw, int group);
 
 // Fixed workspace layout (see lsqb200_workspace_bytes): tickets first, partials after.
 constexpr long long kMaxCounters = 4096;     // channels that may be split across tiles
@@ -44,12 +50,14 @@ struct Tuning {
     int max_tile_kb = 0;        // 0 = no cap; else cap tile bytes (more, smaller tiles)
     int warp_units = 512;       // tiles with <= this many units go to warp groups
     int min_iters = 2;          // never split below min_iters full group iterations
+    int interleave = 1;         // 1: interleave the splits of a channel (grid-stride style), 0: contiguous slices
+    int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
 };
 
 enum : int { K_FWD = 0, K_BWD = 1, K_STATS = 2 };
 
 struct Geometry {
-    int regime, vec, group, splits;
+    int regime, vec, nw, group, splits, interleave;   // nw: 32-bit words per unit (8 / 4 / 2), 0 = scalar path
     long long outer, C, inner;   // after collapsing C == 1
     long long vpr, row_stride, chan_units, units_per_split, tiles, grid;
 };
@@ -57,15 +65,22 @@ struct Geometry {
 inline int elem_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 
 inline Geometry plan_geometry(long long outer, long long C, long long inner, int xdtype, int kind,
-                              bool aligned16, const Tuning& tn) {
+                              int align_bytes, const Tuning& tn, int threads = kThreads, int unroll_override = 0) {
     Geometry g{};
     if (C == 1) { inner *= outer; outer = 1; }      // per-tensor: one contiguous channel
     g.outer = outer; g.C = C; g.inner = inner;
-    const int es = elem_size(xdtype), vfull = 16 / es;
+    const int es = elem_size(xdtype);
     g.regime = (outer == 1) ? 0 : 1;
-    g.vec = vfull;
-    if (!aligned16) g.vec = 1;
-    else if (g.regime == 1 && inner % vfull != 0) g.vec = 1;   // rows would lose 16 B alignment
+    // widest unit (32 / 16 / 8 bytes) the base pointers - and, for strided rows, every row start -
+    // are aligned to; otherwise the scalar path
+    g.nw = 0;
+    for (int ub : {32, 16, 8}) {
+        if (ub > tn.max_unit_bytes || align_bytes % ub != 0) continue;
+        if (g.regime == 1 && (inner * es) % ub != 0) continue;
+        g.nw = ub / 4;
+        break;
+    }
+    g.vec = g.nw ? g.nw * 4 / es : 1;
     if (g.regime == 0) {
         g.vpr = 1LL << 30; g.row_stride = 1LL << 30;   // artificial rows: contiguous, 32-bit walker state
         g.chan_units = (g.vec == 1) ? inner : (inner + g.vec - 1) / g.vec;   // upper bound of the aligned body
@@ -73,11 +88,11 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
         g.vpr = inner / g.vec; g.row_stride = C * g.vpr;
         g.chan_units = outer * g.vpr;
     }
-    const int unroll = kind == K_FWD ? kUnrollFwd : (kind == K_BWD ? kUnrollBwd : kUnrollStats);
+    const int unroll = unroll_override ? unroll_override : (kind == K_FWD ? kUnrollFwd : (kind == K_BWD ? kUnrollBwd : kUnrollStats));
     // how many tiles do we want overall
     const long long target = (long long)tn.sm_count * tn.tiles_per_sm;
     long long splits = (target + C - 1) / C;
-    const long long min_units = (long long)kThreads * unroll * tn.min_iters;
+    const long long min_units = (long long)threads * unroll * tn.min_iters;
     long long max_splits = g.chan_units / min_units;
     if (max_splits < 1) max_splits = 1;
     if (splits > max_splits) splits = max_splits;
@@ -96,15 +111,16 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
     long long ups = (g.chan_units + splits - 1) / splits;
     if (ups < 1) ups = 1;
     // whole group iterations per split keep every split's access pattern identical
-    g.group = (ups <= tn.warp_units) ? 32 : kThreads;
+    g.group = (ups <= tn.warp_units) ? 32 : threads;
     const long long q = (long long)g.group;
     ups = (ups + q - 1) / q * q;
     splits = (g.chan_units + ups - 1) / ups;
     if (splits < 1) splits = 1;
     g.units_per_split = ups;
+    g.interleave = (tn.interleave && splits > 1) ? 1 : 0;
     g.splits = (int)splits;
     g.tiles = C * splits;
-    const long long gpc = kThreads / g.group;
+    const long long gpc = threads / g.group;
     g.grid = (g.tiles + gpc - 1) / gpc;
     return g;
 }
@@ -120,7 +136,12 @@ struct SegArgs {
     int use_grad_scaling, sym;
 };
 
-inline bool is_aligned16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// largest power of two (<= 32) dividing every non-null pointer
+inline int common_alignment(std::initializer_list<const void*> ps) {
+    uintptr_t bits = 32;
+    for (const void* p : ps) if (p) bits |= reinterpret_cast<uintptr_t>(p);
+    return (int)(bits & (~bits + 1));
+}
 
 inline Seg make_seg(const SegArgs& a, const Geometry& g, double* partials, unsigned* counters, long long tile_begin) {
     Seg s;
@@ -138,7 +159,7 @@ inline Seg make_seg(const SegArgs& a, const Geometry& g, double* partials, unsig
     const int bitness = (int)std::ceil(std::log((double)(a.qmax - a.qmin)) / std::log(2.0)) - 1;
     s.stats_denom = (float)std::ldexp(1.0, bitness);
     s.splits = g.splits; s.regime = g.regime; s.per_channel = a.per_channel; s.pdt = a.pdtype;
-    s.sym = a.sym; s.vec = g.vec;
+    s.sym = a.sym; s.vec = g.vec; s.interleave = g.interleave; s.group = g.group;
     return s;
 }
 

@@ -70,12 +70,13 @@ class _PartialWrapper(object):
     def __repr__(self):
         return self.p.__repr__()
 
+    def with_args(self, **kwargs):
+        return _with_args(self, **kwargs)
+
 
 def _with_args(cls_or_self, **kwargs):
     """Class factory: `Foo.with_args(a=1).with_args(b=2)()` builds a fresh Foo(a=1, b=2) each call."""
-    r = _PartialWrapper(partial(cls_or_self, **kwargs))
-    r.with_args = _with_args
-    return r
+    return _PartialWrapper(partial(cls_or_self, **kwargs))
 
 
 class ObserverBase(torch.quantization.observer.ObserverBase):

@@ -1,0 +1,174 @@
+"""Python face of the CPU oracle (oracle/lsq_oracle.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module; the product package (lsqfakequantize-pytorch_b200/torchlsq) never does.
+
+numpy in / numpy out.  16-bit tensors travel as uint16 bit patterns (`to_bits` / `from_bits`
+convert from / to torch tensors).  See the C file's header for the reference lines each
+function follows and for how the oracle is pinned.
+"""
+import ctypes
+import subprocess
+from ctypes import POINTER, Structure, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+F32, F16, BF16 = 0, 1, 2
+CONTRACT_CPU, CONTRACT_CUDA = 0, 3   # reference CPU build (no fusion) / reference CUDA build (v and d fused)
+
+
+class Cfg(Structure):
+    _fields_ = [("quant_min", c_int64), ("quant_max", c_int64), ("type_min", c_int64), ("type_max", c_int64),
+                ("grad_scaler", c_double), ("use_grad_scaling", c_int32), ("sym", c_int32), ("eval_mode", c_int32),
+                ("init_mode", c_int32), ("contract", c_int32), ("numel_div_c", c_int32), ("half_exact", c_int32),
+                ("gs_per_term", c_int32)]
+
+
+_lib = None
+_ref = None
+
+
+def build(force=False):
+    so = HERE / "liblsq_oracle.so"
+    if force or not so.exists() or so.stat().st_mtime < (HERE / "lsq_oracle.c").stat().st_mtime:
+        subprocess.check_call(["make", "-C", str(HERE), "liblsq_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(str(build()))
+        _lib.lsq_oracle_forward.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                            c_int, POINTER(Cfg)]
+        _lib.lsq_oracle_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(Cfg)]
+        _lib.lsq_oracle_weight_init.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64]
+        _lib.lsq_oracle_h2f.restype = c_float
+        _lib.lsq_oracle_h2f.argtypes = [ctypes.c_uint16]
+        _lib.lsq_oracle_f2h.restype = ctypes.c_uint16
+        _lib.lsq_oracle_f2h.argtypes = [c_float]
+        _lib.lsq_oracle_f2bf.restype = ctypes.c_uint16
+        _lib.lsq_oracle_f2bf.argtypes = [c_float]
+    return _lib
+
+
+def cfg(quant_min=0, quant_max=255, type_min=None, type_max=None, use_grad_scaling=True, grad_scaler=1.0,
+        sym=False, eval_mode=False, init_mode=False, contract=CONTRACT_CUDA, numel_div_c=False, half_exact=False,
+        gs_per_term=True):
+    type_min = quant_min if type_min is None else type_min
+    type_max = quant_max if type_max is None else type_max
+    return Cfg(int(quant_min), int(quant_max), int(type_min), int(type_max), float(grad_scaler),
+               int(use_grad_scaling), int(sym), int(eval_mode), int(init_mode), int(contract), int(numel_div_c),
+               int(half_exact), int(gs_per_term))
+
+
+def _dt_of(a: np.ndarray, dt):
+    if dt is not None:
+        return dt
+    if a.dtype == np.float32:
+        return F32
+    if a.dtype == np.float16:
+        return F16
+    raise TypeError("pass dt=BF16/F16 explicitly for uint16 bit patterns")
+
+
+def _raw(a: np.ndarray):
+    """fp16 numpy arrays are reinterpreted as their uint16 bit pattern."""
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint16) if a.dtype == np.float16 else a
+
+
+def _p(a):
+    return a.ctypes.data_as(c_void_p)
+
+
+def _params(scale, shift):
+    s = np.ascontiguousarray(np.asarray(scale, dtype=np.float32).reshape(-1))
+    b = np.ascontiguousarray(np.asarray(shift, dtype=np.float32).reshape(-1))
+    return s, b
+
+
+def forward(x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None):
+    """y with x's dtype / bit pattern.  x is viewed as contiguous (outer, C, inner)."""
+    dt = _dt_of(x, dt)
+    xr = _raw(x)
+    inner = xr.size // (outer * C) if inner is None else inner
+    assert outer * C * inner == xr.size
+    s, b = _params(scale, shift)
+    y = np.empty_like(xr)
+    lib().lsq_oracle_forward(_p(xr), _p(y), dt, _p(s), _p(b), outer, C, inner, int(per_channel), ctypes.byref(c))
+    return y.view(x.dtype) if x.dtype == np.float16 else y
+
+
+def backward(g, x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None, with_abs=False):
+    """(gx, gscale float64[C|1], gshift float64[C|1]): gx in x's dtype; the sums are the exact
+    (double) sums of the reference's fp32 per-element terms.  with_abs=True appends the sums of
+    |terms| (x |gs|), the natural yardstick for the error of any fp32 summation order."""
+    dt = _dt_of(x, dt)
+    xr, gr = _raw(x), _raw(g)
+    inner = xr.size // (outer * C) if inner is None else inner
+    assert outer * C * inner == xr.size == gr.size
+    s, b = _params(scale, shift)
+    nslot = C if per_channel else 1
+    gx = np.empty_like(xr)
+    gs_, gb_ = np.zeros(nslot, np.float64), np.zeros(nslot, np.float64)
+    as_, ab_ = np.zeros(nslot, np.float64), np.zeros(nslot, np.float64)
+    lib().lsq_oracle_backward(_p(gr), _p(xr), _p(gx), dt, _p(s), _p(b), _p(gs_), _p(gb_), _p(as_), _p(ab_),
+                              outer, C, inner, int(per_channel), ctypes.byref(c))
+    gx = gx.view(x.dtype) if x.dtype == np.float16 else gx
+    return (gx, gs_, gb_, as_, ab_) if with_abs else (gx, gs_, gb_)
+
+
+def weight_init(w, quant_min, quant_max, outer=1, C=1, inner=None, dt=None):
+    dt = _dt_of(w, dt)
+    wr = _raw(w)
+    inner = wr.size // (outer * C) if inner is None else inner
+    out = np.empty(C, np.float32)
+    lib().lsq_oracle_weight_init(_p(wr), dt, _p(out), outer, C, inner, int(quant_min), int(quant_max))
+    return out
+
+
+# ---- torch <-> bit-pattern helpers (tests only) ---------------------------------------------
+def to_bits(t):
+    """torch tensor (fp32 / fp16 / bf16, any device) -> (numpy array, dt code)."""
+    import torch
+    t = t.detach().cpu().contiguous()
+    if t.dtype == torch.float32:
+        return t.numpy(), F32
+    if t.dtype == torch.float16:
+        return t.view(torch.int16).numpy().view(np.uint16), F16
+    if t.dtype == torch.bfloat16:
+        return t.view(torch.int16).numpy().view(np.uint16), BF16
+    raise TypeError(t.dtype)
+
+
+def from_bits(a, dt, shape=None):
+    import torch
+    if dt == F32:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).view(torch.float16 if dt == F16 else torch.bfloat16)
+    return t.reshape(shape) if shape is not None else t
+
+
+# ---- the reference's own scalar templates, when oracle/_ref/libref_scalar.so was built ----------
+def ref_scalar():
+    """ctypes handle of oracle/_ref/libref_scalar.so (reference lsq_kernel.h compiled as it lies), or None."""
+    global _ref
+    if _ref is None:
+        so = HERE / "_ref" / "libref_scalar.so"
+        if not so.exists():
+            return None
+        _ref = ctypes.CDLL(str(so))
+        _ref.ref_fwd_tensor_f32.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_float, c_int64, c_int64, c_int64,
+                                            c_int64, c_int]
+        _ref.ref_bwd_tensor_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
+                                            c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_int]
+        _ref.ref_fwd_channel_f32.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                             c_int64, c_int64, c_int64, c_int64, c_int]
+        _ref.ref_bwd_channel_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                             c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_int]
+    return _ref

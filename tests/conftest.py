@@ -1,0 +1,56 @@
+"""Shared test plumbing.  `-m gpu` tests need a B200; everything else runs on CPU.
+
+sys.path: the product package lives in lsqfakequantize-pytorch_b200/ (directory name is not an
+identifier, so it is put on sys.path and imported as `torchlsq`); the oracle is imported as
+`oracle.lsq_oracle` from the repo root (tests only).
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+PKG = ROOT / "lsqfakequantize-pytorch_b200"
+for p in (str(PKG), str(ROOT)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+@pytest.fixture(scope="session")
+def golden_ops():
+    data = np.load(GOLDEN / "ref_cpu_ops.npz")
+    meta = json.loads((GOLDEN / "ref_module_trace.json").read_text())["ops_meta"]
+    cases = {}
+    for name, m in meta.items():
+        cases[name] = dict(meta=m, **{k: data[f"{name}/{k}"] for k in ("x", "g", "scale", "shift", "y", "dx", "ds", "db")})
+    return cases
+
+
+@pytest.fixture(scope="session")
+def golden_module():
+    return json.loads((GOLDEN / "ref_module_trace.json").read_text())
+
+
+@pytest.fixture(scope="session")
+def native_lib():
+    """Build (if needed) and load the C-ABI library; used by CPU symbol tests and GPU tests."""
+    import subprocess
+    so = PKG / "torchlsq" / "libtorchlsq_b200.so"
+    if not so.exists():
+        subprocess.check_call(["make", "-C", str(PKG / "csrc"), "-j8"], stdout=subprocess.DEVNULL)
+    from torchlsq import _cabi
+    return _cabi.load()
+
+
+def geometry(shape, axis):
+    outer = int(np.prod(shape[:axis], dtype=np.int64))
+    inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    return outer, shape[axis], inner

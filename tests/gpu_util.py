@@ -1,0 +1,123 @@
+"""Helpers for the GPU parity tests: call the C ABI (include/lsq_b200.h) on torch CUDA tensors
+and the oracle on the same bits."""
+import numpy as np
+import torch
+
+from oracle import lsq_oracle as O
+from torchlsq import _cabi
+from torchlsq.extension import _DT
+
+DEV = "cuda:0"
+_ws = {}
+
+
+def workspace():
+    lib = _cabi.load()
+    if "ws" not in _ws:
+        _ws["ws"] = torch.zeros(lib.lsqb200_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    return _ws["ws"]
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def qa(qmin=0, qmax=127, tmin=0, tmax=255, use_gs=True, gscaler=1.0, sym=False, eval_mode=False, init_mode=False):
+    return _cabi.qargs(qmin, qmax, tmin, tmax, use_gs, gscaler, sym, eval_mode, init_mode)
+
+
+def ocfg(q, **kw):
+    base = dict(quant_min=q.quant_min, quant_max=q.quant_max, type_min=q.type_min, type_max=q.type_max,
+                use_grad_scaling=bool(q.use_grad_scaling), grad_scaler=q.grad_scaler, sym=bool(q.sym),
+                eval_mode=bool(q.eval_mode), init_mode=bool(q.init_mode), contract=O.CONTRACT_CUDA, numel_div_c=False)
+    base.update(kw)
+    return O.cfg(**base)
+
+
+def fwd(x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False):
+    lib = _cabi.load()
+    y = torch.empty_like(x)
+    inner = x.numel() // (outer * C) if inner is None else inner
+    if per_channel:
+        rc = lib.lsqb200_fwd_channel(x.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
+                                     _DT[x.dtype], _DT[scale.dtype], q, stream())
+    else:
+        rc = lib.lsqb200_fwd_tensor(x.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), x.numel(),
+                                    _DT[x.dtype], _DT[scale.dtype], q, stream())
+    _cabi.check(rc, "fwd")
+    return y
+
+
+def bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, want_gx=True):
+    lib = _cabi.load()
+    gx = torch.empty_like(x) if want_gx else None
+    n = C if per_channel else 1
+    gs = torch.full((n,), float("nan"), dtype=scale.dtype, device=x.device)
+    gb = torch.full((n,), float("nan"), dtype=scale.dtype, device=x.device)
+    ws = workspace()
+    inner = x.numel() // (outer * C) if inner is None else inner
+    gxp = gx.data_ptr() if want_gx else None
+    if per_channel:
+        rc = lib.lsqb200_bwd_channel(g.data_ptr(), x.data_ptr(), gxp, scale.data_ptr(), shift.data_ptr(),
+                                     gs.data_ptr(), gb.data_ptr(), outer, C, inner, _DT[x.dtype], _DT[scale.dtype], q,
+                                     ws.data_ptr(), ws.numel(), stream())
+    else:
+        rc = lib.lsqb200_bwd_tensor(g.data_ptr(), x.data_ptr(), gxp, scale.data_ptr(), shift.data_ptr(),
+                                    gs.data_ptr(), gb.data_ptr(), x.numel(), _DT[x.dtype], _DT[scale.dtype], q,
+                                    ws.data_ptr(), ws.numel(), stream())
+    _cabi.check(rc, "bwd")
+    return gx, gs, gb
+
+
+def same_bits(t: torch.Tensor, ref_np: np.ndarray):
+    """bitwise equality of a CUDA tensor and the oracle's output (NaN payloads ignored)."""
+    a, dt = O.to_bits(t)
+    a = a.reshape(-1)
+    b = np.ascontiguousarray(ref_np).reshape(-1)
+    if dt == O.F32:
+        af, bf = a, b.astype(np.float32, copy=False)
+        nan_a, nan_b = np.isnan(af), np.isnan(bf)
+        return bool(np.array_equal(nan_a, nan_b) and np.array_equal(af.view(np.uint32)[~nan_a], bf.view(np.uint32)[~nan_b]))
+    b = b.view(np.uint16)
+    tt = torch.float16 if dt == O.F16 else torch.bfloat16
+    nan_a = torch.isnan(O.from_bits(a, dt)).numpy()
+    nan_b = torch.isnan(O.from_bits(b, dt)).numpy()
+    return bool(np.array_equal(nan_a, nan_b) and np.array_equal(a[~nan_a], b[~nan_b]))
+
+
+def count_diff(t: torch.Tensor, ref_np: np.ndarray):
+    a, dt = O.to_bits(t)
+    b = np.ascontiguousarray(ref_np).reshape(-1)
+    if dt != O.F32:
+        b = b.view(np.uint16)
+        return int((a.reshape(-1) != b).sum())
+    return int((a.reshape(-1).view(np.uint32) != b.view(np.uint32)).sum())
+
+
+def oracle_fwd(x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, **kw):
+    xb, dt = O.to_bits(x)
+    half_exact = (x.dtype == torch.float16 and scale.dtype == torch.float16)
+    return O.forward(xb.reshape(-1), scale.float().cpu().numpy(), shift.float().cpu().numpy(),
+                     ocfg(q, half_exact=half_exact, **kw), outer, C, inner, per_channel, dt=dt)
+
+
+def oracle_bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, **kw):
+    xb, dt = O.to_bits(x)
+    gb, _ = O.to_bits(g)
+    half_exact = (x.dtype == torch.float16 and scale.dtype == torch.float16)
+    return O.backward(gb.reshape(-1), xb.reshape(-1), scale.float().cpu().numpy(), shift.float().cpu().numpy(),
+                      ocfg(q, half_exact=half_exact, **kw), outer, C, inner, per_channel, dt=dt, with_abs=True)
+
+
+def assert_grads_close(mine: torch.Tensor, ref: np.ndarray, mag: np.ndarray, rel, what=""):
+    """|mine - ref| <= rel*|ref| + 3e-8*sum|terms| + output rounding.
+
+    The second term is the cancellation floor of the streaming kernels: their per-thread fp32
+    partial sums (<= 32 terms each, then fp64) are good to ~2^-24 of the summed magnitude; the
+    reference's fp32 at::sum is ~10x looser.  Warp-group kernels accumulate in fp64 throughout."""
+    m = mine.double().cpu().numpy()
+    eps_out = {torch.float32: 2.0 ** -24, torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}[mine.dtype]
+    tol = rel * np.abs(ref) + 3e-8 * mag + eps_out * np.abs(ref) + 1e-30
+    bad = ~(np.abs(m - ref) <= tol)
+    bad &= ~(np.isnan(m) & np.isnan(ref))
+    assert not bad.any(), (what, m[bad][:5], ref[bad][:5], tol[bad][:5])

@@ -1,0 +1,210 @@
+"""Host-side logic that needs no GPU: functional.lsq argument handling, operator registration,
+error behaviour on CPU tensors, LSQFakeQuantizer ranges / toggles / state machine against the
+traces recorded from the reference module (tests/golden/ref_module_trace.json)."""
+import pytest
+import torch
+
+import torchlsq
+from torchlsq import LSQFakeQuantizer
+from torchlsq.functional import lsq
+from torchlsq.quantized.modules import observers as obs
+
+
+def test_ops_registered_with_reference_schemas():
+    assert torchlsq.extension._HAS_OPS and torchlsq.extension._has_ops()
+    tail = ("int quant_min, int quant_max, int type_min, int type_max, bool use_grad_scaling, float grad_scaler, "
+            "bool sym, bool eval_mode, bool init_mode")
+    want = {
+        "lsq_forward_per_tensor": f"torchlsq::lsq_forward_per_tensor(Tensor x, Tensor scale, Tensor shift, {tail}) -> Tensor",
+        "lsq_backward_per_tensor": f"torchlsq::lsq_backward_per_tensor(Tensor grad, Tensor x, Tensor scale, Tensor shift, {tail}) -> (Tensor, Tensor, Tensor)",
+        "lsq_forward_per_channel": f"torchlsq::lsq_forward_per_channel(Tensor x, Tensor scale, Tensor shift, int axis, {tail}) -> Tensor",
+        "lsq_backward_per_channel": f"torchlsq::lsq_backward_per_channel(Tensor grad, Tensor x, Tensor scale, Tensor shift, int axis, {tail}) -> (Tensor, Tensor, Tensor)",
+    }
+    for name, schema in want.items():
+        assert str(getattr(torch.ops.torchlsq, name).default._schema) == schema
+    s = str(torch.ops.torchlsq.lsq.default._schema)
+    assert s.count("Tensor") == 4 and s.count("int") == 5 and s.count("bool") == 5 and "float" in s
+    assert torch.ops.torchlsq._cuda_version() // 1000 == 12
+    assert torchlsq.extension._check_cuda_version() == torch.ops.torchlsq._cuda_version()
+
+
+def test_no_cpu_fallback():
+    x = torch.randn(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        lsq(x, torch.ones(1), torch.zeros(1))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        torch.ops.torchlsq.lsq_backward_per_tensor(x, x, torch.ones(1), torch.zeros(1), 0, 127, 0, 255, True, 1.0,
+                                                   False, False, False)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        lsq(x, torch.ones(3), torch.zeros(3), is_perchannel=True, axis=1)
+
+
+def test_functional_argument_checks():
+    x = torch.randn(4, 3)
+    with pytest.raises(AssertionError, match="symmetric"):
+        lsq(x, torch.ones(1), torch.zeros(1), quant_min=1, quant_max=5, is_affine=False)
+    with pytest.raises(RuntimeError, match="1-D tensor"):
+        lsq(x, torch.tensor(1.0), torch.zeros(1))
+    with pytest.raises(RuntimeError, match="1-D tensor"):
+        lsq(x, torch.ones(1), torch.zeros(1, 1))
+
+
+def test_qranges_match_reference(golden_module):
+    kw = {
+        "act_default": dict(otype='activation'),
+        "act_8bit": dict(otype='activation', avoid_torch_overflow=False),
+        "act_sym": dict(otype='activation', qscheme=torch.per_tensor_symmetric),
+        "act_custom": dict(otype='activation', quant_min=0, quant_max=15),
+        "w_default": dict(otype='weight', dtype=torch.qint8, qscheme=torch.per_channel_symmetric),
+        "w_8bit": dict(otype='weight', dtype=torch.qint8, qscheme=torch.per_tensor_symmetric, avoid_torch_overflow=False),
+        "w_custom": dict(otype='weight', dtype=torch.qint8, qscheme=torch.per_tensor_symmetric, quant_min=-7, quant_max=8,
+                         init_scale=0.5),
+    }
+    for tag, ref in golden_module["qranges"].items():
+        m = LSQFakeQuantizer(None, init_mode='learnable', **kw[tag])
+        got = dict(quant_min=m.quant_min, quant_max=m.quant_max, init_shift=m.init_shift, ch_axis=m.ch_axis,
+                   n_batches=m.n_batches)
+        assert got == ref, tag
+
+
+def test_constructor_asserts():
+    with pytest.raises(AssertionError):
+        LSQFakeQuantizer(None, 'weight', dtype=torch.qint8, qscheme=torch.per_tensor_affine, init_mode='learnable')
+    with pytest.raises(AssertionError):
+        LSQFakeQuantizer(None, 'weight', dtype=torch.quint8, qscheme=torch.per_tensor_symmetric, init_mode='learnable')
+    with pytest.raises(AssertionError):
+        LSQFakeQuantizer(None, 'activation', dtype=torch.qint8, init_mode='learnable')
+    with pytest.raises(AssertionError):
+        LSQFakeQuantizer(None, 'activation', init_mode='nope')
+    with pytest.raises(AssertionError):
+        LSQFakeQuantizer(None, 'activation', init_mode='learnable', quant_min=0, quant_max=255)   # > 7 bit
+    with pytest.raises(AssertionError):
+        LSQFakeQuantizer(torch.quantization.MinMaxObserver(), 'activation', init_mode='observer')   # instance, not class
+
+
+def test_with_args_factory_works():
+    """the reference raises NameError here (functools.partial never imported)."""
+    f = LSQFakeQuantizer.with_args(observer=torch.quantization.MovingAverageMinMaxObserver, otype='activation',
+                                   init_batches=5)
+    a, b = f(), f()
+    assert a is not b and a.n_batches == 5 and isinstance(a.activation_post_process,
+                                                          torch.quantization.MovingAverageMinMaxObserver)
+    g = f.with_args(grad_scaler=2.0)
+    assert g().grad_scaler == 2.0
+
+
+def test_toggles_and_state_dict_keys():
+    m = LSQFakeQuantizer(torch.quantization.MovingAverageMinMaxObserver, 'activation')
+    assert set(m.state_dict().keys()) >= {"fake_quant_enabled", "observer_enabled", "learning_enabled", "current_batch"}
+    assert int(m.observer_enabled[0]) == 1
+    m.enable_param_learning()
+    assert int(m.learning_enabled[0]) == 1 and int(m.observer_enabled[0]) == 0 and m.n_batches == -1
+    m.enable_static_estimate()
+    assert int(m.learning_enabled[0]) == 0 and int(m.observer_enabled[0]) == 1
+    m.disable_fake_quant()
+    assert int(m.fake_quant_enabled[0]) == 0
+    torchlsq.enable_fake_quant(m)
+    assert int(m.fake_quant_enabled[0]) == 1
+    torchlsq.disable_observer(m)
+    assert int(m.observer_enabled[0]) == 0
+    torchlsq.enable_observer_on_weights(m)       # quint8 module: not a weight quantizer -> untouched
+    assert int(m.observer_enabled[0]) == 0
+    torchlsq.disable_fake_quant_on_act(m)
+    assert int(m.fake_quant_enabled[0]) == 0
+    # mirrors follow load_state_dict
+    sd = m.state_dict()
+    sd["current_batch"] = torch.tensor([77])
+    m.load_state_dict(sd)
+    assert m._m_batch == 77 and m._m_fq == 0
+
+
+def test_calculate_qparams_and_zp_conversion():
+    m = LSQFakeQuantizer(None, 'activation', init_mode='learnable', init_scale=0.5, init_shift=-3.2)
+    s, zp = m.calculate_qparams(verbose=False)
+    assert s == 0.5 and zp == 6          # round(3.2 / 0.5) = round(6.4)
+    zp = LSQFakeQuantizer.convert_shift_to_zp(torch.tensor([-1000.0, 0.3, 1.25]), torch.tensor([0.5, 0.1, 0.5]), torch.quint8)
+    assert zp.tolist() == [255, 0, 0] and zp.dtype == torch.int64
+    zp = LSQFakeQuantizer.convert_shift_to_zp(torch.tensor([1000.0, -1.25]), torch.tensor([0.5, 0.5]), torch.qint8)
+    assert zp.tolist() == [-128, 2]      # round-half-even of 2.5
+
+
+class _Spy:
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, x, scale, shift, qmin, qmax, tmin, tmax, axis, use_gs, gscaler, is_affine, is_perchannel,
+                 eval_mode=False, init_mode=False):
+        self.calls.append(dict(qmin=qmin, qmax=qmax, tmin=tmin, tmax=tmax, axis=axis, use_gs=use_gs, gscaler=gscaler,
+                               is_affine=is_affine, is_perchannel=is_perchannel, eval_mode=bool(eval_mode),
+                               init_mode=bool(init_mode), scale_rg=bool(scale.requires_grad),
+                               shift_rg=bool(shift.requires_grad)))
+        return x * 1.0
+
+
+def _run_trace(monkeypatch, build, steps, train_flags=None, x_shape=(4, 6), weight=False):
+    spy = _Spy()
+    monkeypatch.setattr(obs, "lsq", spy)
+    if weight:   # the mu+-3sigma kernel needs a GPU; the state machine does not care about the values
+        monkeypatch.setattr(obs, "weight_init_scale",
+                            lambda w, ax, pc, qmin, qmax: torch.full((w.shape[ax] if pc else 1,), 0.01))
+    torch.manual_seed(7)
+    m = build()
+    rec = []
+    for i in range(steps):
+        m.train(train_flags[i] if train_flags else True)
+        spy.calls.clear()
+        x = torch.randn(*x_shape) + 0.5
+        out = m(x)
+        rec.append(dict(step=i, identity=bool(out is x), call=(dict(spy.calls[0]) if spy.calls else None),
+                        observer_enabled=int(m.observer_enabled[0]), current_batch=int(m.current_batch[0]),
+                        n_batches=int(m.n_batches)))
+    return rec
+
+
+def _compare(rec, ref):
+    assert len(rec) == len(ref)
+    for a, b in zip(rec, ref):
+        for k in ("step", "identity", "observer_enabled", "current_batch", "n_batches"):
+            assert a[k] == b[k], (a["step"], k, a[k], b[k])
+        assert (a["call"] is None) == (b["call"] is None), a["step"]
+        if a["call"]:
+            for k, v in a["call"].items():
+                assert v == b["call"][k], (a["step"], k, v, b["call"][k])
+
+
+MA = torch.quantization.MovingAverageMinMaxObserver
+
+
+@pytest.mark.parametrize("name,build,steps,flags,shape,weight", [
+    ("act_learnable_n3", lambda: LSQFakeQuantizer(None, 'activation', init_mode='learnable', init_batches=3), 8, None, (4, 6), False),
+    ("act_observer_n2", lambda: LSQFakeQuantizer(MA, 'activation', init_mode='observer', init_batches=2), 7, None, (4, 6), False),
+    ("act_observer_static", lambda: LSQFakeQuantizer(MA, 'activation', init_mode='observer', init_batches=2, learn_params=False), 5, None, (4, 6), False),
+    ("act_learnable_evalmix", lambda: LSQFakeQuantizer(None, 'activation', init_mode='learnable', init_batches=2), 7,
+     [True, True, False, True, True, False, True], (4, 6), False),
+    ("weight_sym", lambda: LSQFakeQuantizer(None, 'weight', dtype=torch.qint8, qscheme=torch.per_channel_symmetric, init_mode='learnable'), 4, None, (6, 4, 3, 3), True),
+    ("weight_sym_8bit_tensor", lambda: LSQFakeQuantizer(None, 'weight', dtype=torch.qint8, qscheme=torch.per_tensor_symmetric, init_mode='learnable', avoid_torch_overflow=False), 3, None, (6, 4, 3, 3), True),
+])
+def test_state_machine_matches_reference_trace(monkeypatch, golden_module, name, build, steps, flags, shape, weight):
+    rec = _run_trace(monkeypatch, build, steps, flags, shape, weight)
+    _compare(rec, golden_module["traces"][name])
+
+
+def test_observer_mode_copies_observer_qparams(monkeypatch, golden_module):
+    """scale / shift written by `_set_weights` from the torch observer, step by step, vs the reference."""
+    spy = _Spy()
+    seen = []
+
+    def spy2(x, scale, shift, *a, **k):
+        seen.append(([float(v) for v in scale.detach().reshape(-1)[:4]], [float(v) for v in shift.detach().reshape(-1)[:4]]))
+        return spy(x, scale, shift, *a, **k)
+
+    monkeypatch.setattr(obs, "lsq", spy2)
+    torch.manual_seed(7)
+    m = LSQFakeQuantizer(MA, 'activation', init_mode='observer', init_batches=2)
+    for i in range(7):
+        m.train(True)
+        m(torch.randn(4, 6) + 0.5)
+    ref = [r["call"] for r in golden_module["traces"]["act_observer_n2"] if r["call"]]
+    assert len(seen) == len(ref)
+    for (s, b), r in zip(seen, ref):
+        assert s == pytest.approx(r["scale"], rel=1e-6) and b == pytest.approx(r["shift"], rel=1e-6, abs=1e-7)
