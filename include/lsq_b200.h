@@ -150,8 +150,9 @@ typedef struct lsqb200_launch_info {
 /* Geometry the library would pick for a (outer, C, inner) tensor; pure host computation. */
 LSQB200_API int lsqb200_query_launch(int64_t outer, int64_t C, int64_t inner, int xdtype, int backward,
                          int aligned16, lsqb200_launch_info* out);
-/* Override tuning knobs (NULL / "" restores defaults).  Format "threads=256,unroll=4,occ=4,
- * tile_kb=512".  For experiments; not part of the reference surface. */
+/* Override launch-geometry knobs (NULL / "" restores defaults), e.g.
+ * "fwd_tile_kb=32,bwd_tile_kb=256,interleave=1,max_unit_bytes=32".  For experiments
+ * (also read once from $LSQB200_TUNE); not part of the reference surface. */
 LSQB200_API int lsqb200_set_tuning(const char* spec);
 
 #ifdef __cplusplus

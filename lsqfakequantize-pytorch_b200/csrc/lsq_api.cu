@@ -261,8 +261,11 @@ int lsqb200_set_tuning(const char* spec) {
         if (eq == std::string::npos) return fail(LSQB200_ERR_ARG, "tuning spec: expected key=value");
         const std::string k = kv.substr(0, eq);
         const int v = std::atoi(kv.c_str() + eq + 1);
-        if (k == "tiles_per_sm") g_tuning.tiles_per_sm = v;
-        else if (k == "max_tile_kb") g_tuning.max_tile_kb = v;
+        if (k == "fwd_tile_kb") g_tuning.fwd_tile_kb = v;
+        else if (k == "bwd_tile_kb") g_tuning.bwd_tile_kb = v;
+        else if (k == "stats_tile_kb") g_tuning.stats_tile_kb = v;
+        else if (k == "fwd_min_tiles_per_sm") g_tuning.fwd_min_tiles_per_sm = v;
+        else if (k == "bwd_min_tiles_per_sm") g_tuning.bwd_min_tiles_per_sm = v;
         else if (k == "warp_units") g_tuning.warp_units = v;
         else if (k == "min_iters") g_tuning.min_iters = v;
         else if (k == "sm_count") g_tuning.sm_count = v;
@@ -271,7 +274,8 @@ int lsqb200_set_tuning(const char* spec) {
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;
     }
-    if (g_tuning.tiles_per_sm < 1 || g_tuning.min_iters < 1 || g_tuning.sm_count < 1 || g_tuning.warp_units < 0) {
+    if (g_tuning.fwd_tile_kb < 1 || g_tuning.bwd_tile_kb < 1 || g_tuning.stats_tile_kb < 1 || g_tuning.min_iters < 1 ||
+        g_tuning.sm_count < 1 || g_tuning.warp_units < 0 || g_tuning.fwd_min_tiles_per_sm < 1 || g_tuning.bwd_min_tiles_per_sm < 1) {
         g_tuning = Tuning();
         g_tuning.sm_count = sms;
         return fail(LSQB200_ERR_ARG, "tuning spec: value out of range");

@@ -249,9 +249,9 @@ __device__ __forceinline__ float fq_forward(float x, const Chan& c) {
 //   * the border factor (xq <= qmin ? qmin - zp : qmax - zp) IS r - zp, because outside the
 //     open range the clamped, rounded r equals qmin or qmax exactly (NaN -> qmax, as in the
 //     reference where fmin drops the NaN first);
-//   * interior term g'*(xfq - x)*inv_s is formed as g' * ((xfq - x)*inv_s) and fused into the
-//     accumulation (<= 2 ulp per term from the reference's left-to-right product; only sums
-//     are observable and they are held to 1e-6);
+//   * in the streaming kernels the interior term g'*(xfq - x)*inv_s is formed as
+//     g' * ((xfq - x)*inv_s) and fused into the accumulation (<= 2 ulp per term from the
+//     reference's left-to-right product; only sums are observable and they are held to 1e-6);
 //   * dB = (!mask) * g' is exact, so fma(g', 1 - m, acc) adds exactly the reference's term.
 // ACC is float for the streaming kernels (<= UNROLL*VEC terms per partial, then promoted to
 // double) and double for the warp-group kernels that own short channels.
@@ -266,13 +266,17 @@ __device__ __forceinline__ float fq_backward(float g, float x, const Chan& c, AC
         const float t = __fsub_rn(rintf(xq), c.zp);
         const float d = __fmaf_rn(t, c.s, -x);                     // xfq - x, fused as in the reference build
         const float gg = (BMODE == B_INIT) ? __fmul_rn(2.0f, d) : g;
-        const float w = mask ? __fmul_rn(d, c.inv_s) : t;
         const float nm = __fsub_rn(1.0f, m);
         if (sizeof(ACC) == 4) {
+            // streaming kernels: one select + two fused accumulations
+            const float w = mask ? __fmul_rn(d, c.inv_s) : t;
             accS = __fmaf_rn(gg, w, accS);
             accB = __fmaf_rn(gg, nm, accB);
         } else {
-            accS += (ACC)__fmul_rn(gg, w);
+            // warp-group kernels (short channels): the reference's fp32 terms bit for bit,
+            // (g'*d)*inv_s or g'*(r - zp), summed in double
+            const float dS = mask ? __fmul_rn(__fmul_rn(gg, d), c.inv_s) : __fmul_rn(gg, t);
+            accS += (ACC)dS;
             accB += (ACC)__fmul_rn(gg, nm);
         }
     }

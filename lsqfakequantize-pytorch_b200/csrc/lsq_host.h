@@ -13,14 +13,17 @@ namespace lsqb200 {
 
 // Compile-time launch shape of the product kernels (tools/tune.cu instantiates alternatives).
 constexpr int kThreads = 256;
-constexpr int kUnrollFwd = 4;
-constexpr int kUnrollBwd = 4;
+// Launch shapes picked from the round-1 sweep on B200 (profiles/r1_tune_sweep.md): 256-thread
+// CTAs, ONE 256-bit unit in flight per thread and operand (two 128-bit units on the narrower
+// path), 8 resident CTAs/SM forward and 4 backward.
+constexpr int kUnrollFwd = 2;
+constexpr int kUnrollBwd = 2;
 constexpr int kUnrollStats = 4;
 // units in flight per thread and operand: keep ~64 bytes per operand whatever the unit width
 constexpr int unroll_for(int base, int nw) { return nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base; }
 constexpr int kMinBlocksStats = 2;
-constexpr int kMinBlocksFwd = 4;   // __launch_bounds__ min CTAs/SM -> register cap 64
-constexpr int kMinBlocksBwd = 3;   // -> register cap 85
+constexpr int kMinBlocksFwd = 8;   // __launch_bounds__ min CTAs/SM -> register cap 32
+constexpr int kMinBlocksBwd = 4;   // -> register cap 64
 constexpr int kLd = LD_NC_NOALLOC;   // streaming loads: read-only path, no L1 allocation
 constexpr int kSt = ST_DEFAULT;
 
@@ -46,10 +49,17 @@ constexpr size_t kWorkspaceBytes = kMaxCounters * 4 + kMaxSplitTiles * 16;
 
 struct Tuning {
     int sm_count = 148;
-    int tiles_per_sm = 16;      // target tiles (of a big tensor) per SM
-    int max_tile_kb = 0;        // 0 = no cap; else cap tile bytes (more, smaller tiles)
+    // Tile = the slice of one channel a thread group owns.  Small tiles keep all SMs busy to the
+    // end of the launch (SMs do not progress at the same speed; a single wave of big equal
+    // slices costs ~10 %); the backward pays one block reduction + ticket per tile, so its
+    // tiles are larger.  Sizes are bytes of ONE operand.
+    int fwd_tile_kb = 32;
+    int bwd_tile_kb = 256;
+    int stats_tile_kb = 128;
+    int fwd_min_tiles_per_sm = 16;   // small tensors: shrink tiles until the machine is full
+    int bwd_min_tiles_per_sm = 8;
     int warp_units = 512;       // tiles with <= this many units go to warp groups
-    int min_iters = 2;          // never split below min_iters full group iterations
+    int min_iters = 1;          // never split below min_iters full group iterations
     int interleave = 1;         // 1: interleave the splits of a channel (grid-stride style), 0: contiguous slices
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
 };
@@ -89,18 +99,19 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
         g.chan_units = outer * g.vpr;
     }
     const int unroll = unroll_override ? unroll_override : (kind == K_FWD ? kUnrollFwd : (kind == K_BWD ? kUnrollBwd : kUnrollStats));
-    // how many tiles do we want overall
-    const long long target = (long long)tn.sm_count * tn.tiles_per_sm;
-    long long splits = (target + C - 1) / C;
+    // how many tiles: by size, but at least enough to fill the machine
+    const long long unit_bytes = g.nw ? g.nw * 4 : es;
+    const int tile_kb = kind == K_FWD ? tn.fwd_tile_kb : (kind == K_BWD ? tn.bwd_tile_kb : tn.stats_tile_kb);
+    long long tile_units = (long long)tile_kb * 1024 / unit_bytes;
+    if (tile_units < 1) tile_units = 1;
+    const long long min_total = (long long)tn.sm_count * (kind == K_FWD ? tn.fwd_min_tiles_per_sm : tn.bwd_min_tiles_per_sm);
+    long long splits = (g.chan_units + tile_units - 1) / tile_units;
+    const long long by_fill = (min_total + C - 1) / C;
+    if (splits < by_fill) splits = by_fill;
     const long long min_units = (long long)threads * unroll * tn.min_iters;
     long long max_splits = g.chan_units / min_units;
     if (max_splits < 1) max_splits = 1;
     if (splits > max_splits) splits = max_splits;
-    if (tn.max_tile_kb > 0) {
-        const long long cap_units = (long long)tn.max_tile_kb * 1024 / ((long long)g.vec * es);
-        const long long s2 = (g.chan_units + cap_units - 1) / cap_units;
-        if (s2 > splits) splits = s2;
-    }
     if (kind == K_FWD) {
         // no reduction: nothing limits the split count but launch granularity
     } else {
@@ -111,7 +122,10 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
     long long ups = (g.chan_units + splits - 1) / splits;
     if (ups < 1) ups = 1;
     // whole group iterations per split keep every split's access pattern identical
-    g.group = (ups <= tn.warp_units) ? 32 : threads;
+    // warp groups own whole short channels (conv-weight rows, small-map activations); anything
+    // longer is streamed by CTA groups
+    g.group = (g.chan_units <= tn.warp_units) ? 32 : threads;
+    if (g.group == 32) ups = g.chan_units > 0 ? g.chan_units : 1;
     const long long q = (long long)g.group;
     ups = (ups + q - 1) / q * q;
     splits = (g.chan_units + ups - 1) / ups;

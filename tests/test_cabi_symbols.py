@@ -63,8 +63,8 @@ def test_launch_geometry_is_pure_host_logic(native_lib):
     assert native_lib.lsqb200_query_launch(1, 1, 100000, 0, 0, 0, ctypes.byref(info)) == 0
     assert info.vec == 1
     assert native_lib.lsqb200_query_launch(-1, 1, 1, 0, 0, 1, ctypes.byref(info)) == -1
-    assert native_lib.lsqb200_set_tuning(b"tiles_per_sm=4") == 0
+    assert native_lib.lsqb200_set_tuning(b"bwd_tile_kb=4096,max_unit_bytes=16,bwd_min_tiles_per_sm=1") == 0
     assert native_lib.lsqb200_query_launch(1, 1, 1 << 28, 0, 1, 1, ctypes.byref(info)) == 0
-    assert info.splits <= 148 * 4 + 1
+    assert info.vec == 4 and info.splits == (1 << 30) // (4096 * 1024)
     assert native_lib.lsqb200_set_tuning(b"bogus=1") == -1
     assert native_lib.lsqb200_set_tuning(None) == 0

@@ -2,7 +2,7 @@
 // Not part of the product library: it includes the same device code (lsq_device.cuh) and the
 // same host planner (lsq_host.h) and instantiates ALTERNATIVE (threads, unroll, min-blocks,
 // load policy, store policy) variants, times them with CUDA events on big L2-defeating buffers
-// and prints one CSV line per (variant, tiles_per_sm).  Build + run:  make -C tools && tools/tune
+// and prints one CSV line per (variant, tile size).  Build + run:  make -C tools && tools/tune
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -94,7 +94,7 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     printf("# device sms=%d buffer=%zu MiB reps=%d\n", sms, bytes >> 20, reps);
-    printf("kind,dtype,nw,threads,unroll,minb,ld,st,interleave,tiles_per_sm,occ_ctas_per_sm,regs,grid,ms_best,ms_med,GBps_best,GBps_med\n");
+    printf("kind,dtype,nw,threads,unroll,minb,ld,st,interleave,tile_kb,occ_ctas_per_sm,regs,grid,ms_best,ms_med,GBps_best,GBps_med\n");
 
     // reference points: cudaMemcpy D2D and a plain uint4 grid-stride copy
     {
@@ -128,14 +128,13 @@ int main(int argc, char** argv) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)v.fn, v.threads, 0));
         const int es = v.xdtype == DT_F32 ? 4 : 2;
         const long long n = (long long)(bytes / es);
-        for (int il : {0, 1})
-        for (int tps : {1, 2, 4, 8, 16, 32}) {
+        for (int il : {1, 0})
+        for (int tps : {8, 16, 32, 64, 128, 256, 512, 2048}) {   // tile size in KB of one operand
+            if (il == 0 && tps != 32 && tps != 256) continue;
             Tuning tn;
             tn.interleave = il;
             tn.sm_count = sms;
-            // tps == 0: exactly one full wave at the kernel's real occupancy; k: k tiles per resident slot
-            tn.tiles_per_sm = tps == 0 ? occ : occ * tps;
-            if (tps == 0 && occ == 0) continue;
+            tn.fwd_tile_kb = tn.bwd_tile_kb = tps;
             tn.max_unit_bytes = v.unit_bytes;
             Geometry geo = plan_geometry(1, 1, n, v.xdtype, v.kind, 32, tn, v.threads, v.unroll);
             SegArgs a{};
