@@ -81,8 +81,17 @@ SegArgs seg_args(const void* x, void* y, const void* g, void* gx, const void* sc
 int launch(KernelFn k, const Seg& seg, const Seg* table, int nseg, long long tiles, long long grid, cudaStream_t st) {
     if (grid <= 0) return 0;
     if (grid > 2147483647LL) return fail(LSQB200_ERR_ARG, "tensor too large for one launch");
-    k<<<(unsigned)grid, kThreads, 0, st>>>(seg, table, nseg, tiles);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with the previous kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tuning().pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, seg, table, nseg, tiles);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return 0;
 }
@@ -271,6 +280,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "sm_count") g_tuning.sm_count = v;
         else if (k == "max_unit_bytes") g_tuning.max_unit_bytes = v;
         else if (k == "interleave") g_tuning.interleave = v;
+        else if (k == "pdl") g_tuning.pdl = v;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;
     }

@@ -320,6 +320,12 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, double* sm /* [
 template <int G, int THREADS>
 __device__ __forceinline__ bool stage_segment(const Seg& single, const Seg* table, int nseg,
                                               long long gtile, long long total_tiles, Seg* dst_seg) {
+    // Programmatic dependent launch (sm_90+): let the NEXT kernel of the stream start launching
+    // while this grid drains, and - when this grid itself was launched as a dependent - wait
+    // for the previous grid to complete before touching any global memory.  Both are no-ops
+    // for ordinary launches.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (gtile >= total_tiles) return false;      // whole group exits together (G == THREADS: never)
     const int tg = threadIdx.x % G;
     uint32_t* dst = reinterpret_cast<uint32_t*>(dst_seg);

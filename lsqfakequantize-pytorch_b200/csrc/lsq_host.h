@@ -61,6 +61,7 @@ struct Tuning {
     int warp_units = 512;       // tiles with <= this many units go to warp groups
     int min_iters = 1;          // never split below min_iters full group iterations
     int interleave = 1;         // 1: interleave the splits of a channel (grid-stride style), 0: contiguous slices
+    int pdl = 1;                // launch with programmatic stream serialization (prologue overlaps predecessor's tail)
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
 };
 
