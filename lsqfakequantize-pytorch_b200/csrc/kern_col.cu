@@ -1,0 +1,50 @@
+// kern_col.cu -- instantiations of the column-layout (short channel rows) kernels.
+// Variants (unit words, rows in flight, min CTAs/SM fwd / bwd): 0 = (4, 2, 4/2), 1 = (4, 4, 3/2), 2 = (2, 4, 6/4), 3 = (2, 8, 4/3)
+#include "lsq_column.cuh"
+#include "lsq_host.h"
+namespace lsqb200 {
+namespace {
+template <typename T, int MODE, int CNW, int U, int MBF, int MBB>
+struct V {
+    static ColKernelFn f(bool init) {
+        return init ? lsq_col_fwd_kernel<T, MODE, true, CNW, U, MBF, kLd, kSt> : lsq_col_fwd_kernel<T, MODE, false, CNW, U, MBF, kLd, kSt>;
+    }
+    static ColKernelFn b(int bmode) {
+        switch (bmode) {
+            case B_NORMAL: return lsq_col_bwd_kernel<T, MODE, B_NORMAL, CNW, U, MBB, kLd, kSt>;
+            case B_INIT: return lsq_col_bwd_kernel<T, MODE, B_INIT, CNW, U, MBB, kLd, kSt>;
+            case B_EVAL: return lsq_col_bwd_kernel<T, MODE, B_EVAL, CNW, U, MBB, kLd, kSt>;
+            default: return lsq_col_bwd_kernel<T, MODE, B_EVAL_INIT, CNW, U, MBB, kLd, kSt>;
+        }
+    }
+};
+template <typename T, int MODE>
+ColKernelFn pick_f(bool init, int v) {
+    switch (v) {
+        case 1: return V<T, MODE, 4, 4, 3, 2>::f(init);
+        case 2: return V<T, MODE, 2, 4, 6, 4>::f(init);
+        case 3: return V<T, MODE, 2, 8, 4, 3>::f(init);
+        default: return V<T, MODE, 4, 2, 4, 2>::f(init);
+    }
+}
+template <typename T, int MODE>
+ColKernelFn pick_b(int bmode, int v) {
+    switch (v) {
+        case 1: return V<T, MODE, 4, 4, 3, 2>::b(bmode);
+        case 2: return V<T, MODE, 2, 4, 6, 4>::b(bmode);
+        case 3: return V<T, MODE, 2, 8, 4, 3>::b(bmode);
+        default: return V<T, MODE, 4, 2, 4, 2>::b(bmode);
+    }
+}
+}  // namespace
+ColKernelFn get_col_fwd_kernel(int xdtype, int mode, bool init, int v) {
+    if (xdtype == DT_F32) return pick_f<float, M_FP32>(init, v);
+    if (xdtype == DT_BF16) return pick_f<__nv_bfloat16, M_FP32>(init, v);
+    return mode == M_HALF_EXACT ? pick_f<__half, M_HALF_EXACT>(init, v) : pick_f<__half, M_FP32>(init, v);
+}
+ColKernelFn get_col_bwd_kernel(int xdtype, int mode, int bmode, int v) {
+    if (xdtype == DT_F32) return pick_b<float, M_FP32>(bmode, v);
+    if (xdtype == DT_BF16) return pick_b<__nv_bfloat16, M_FP32>(bmode, v);
+    return mode == M_HALF_EXACT ? pick_b<__half, M_HALF_EXACT>(bmode, v) : pick_b<__half, M_FP32>(bmode, v);
+}
+}  // namespace lsqb200

@@ -15,6 +15,7 @@
 
 #include "../../include/lsq_b200.h"
 #include "lsq_host.h"
+#include "lsq_column.cuh"
 
 using namespace lsqb200;
 
@@ -98,6 +99,81 @@ int launch(KernelFn k, const Seg& seg, const Seg* table, int nseg, long long til
 
 size_t param_size(int pdt) { return pdt == DT_F32 ? 4 : 2; }
 
+// ---- column-layout path (short channel rows: channels-last, 7x7 / 14x14 maps) ------------------
+struct ColGeom { bool ok; int tx, ty; long long units_per_row, rows_per_split, col_blocks, row_splits; };
+
+// resident CTAs per SM of a kernel (cached per function)
+int occupancy_of(const void* fn, int threads) {
+    static std::mutex mu;
+    static std::map<const void*, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(fn);
+    if (it != cache.end()) return it->second;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, threads, 0) != cudaSuccess || occ < 1) occ = 2;
+    cache[fn] = occ;
+    return occ;
+}
+
+ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_bytes, const Tuning& tn, int occ) {
+    ColGeom g{};
+    const int ub = kColVariantNW[tn.col_variant] * 4;
+    const int es = elem_size(xdt), vec = ub / es;
+    const long long L = C * inner;
+    g.ok = tn.column_path && outer > 1 && C > 1 && C <= kMaxColumnChannels && L < (1LL << 31) && align_bytes % 16 == 0 && (L * es) % 16 == 0 &&
+           ((inner * es) % 16 != 0 || inner * es < tn.column_max_row_bytes);
+    if (!g.ok) return g;
+    g.units_per_row = L / vec;
+    int tx = 1;
+    while (tx < kColThreads && tx < g.units_per_row) tx <<= 1;
+    g.tx = tx; g.ty = kColThreads / tx;
+    g.col_blocks = (g.units_per_row + tx - 1) / tx;
+    // whole waves of CTAs (col_waves per resident slot); the per-thread set-up (2*VEC parameter loads,
+    // VEC divisions) is amortised over every row a thread visits
+    const long long slots = (long long)tn.sm_count * occ;
+    long long splits = ((long long)tn.col_waves * slots + g.col_blocks - 1) / g.col_blocks;
+    if (splits < 1) splits = 1;
+    long long rows_pt = (outer + splits * g.ty - 1) / (splits * g.ty);
+    if (rows_pt < 2) rows_pt = 2;
+    g.rows_per_split = rows_pt * g.ty;
+    g.row_splits = (outer + g.rows_per_split - 1) / g.rows_per_split;
+    if (g.row_splits > 65535) { g.rows_per_split = (outer + 65534) / 65535; g.row_splits = (outer + g.rows_per_split - 1) / g.rows_per_split; }
+    return g;
+}
+
+ColSeg make_colseg(const ColGeom& g, const void* x, void* y, const void* grad, void* gx, const void* scale, const void* shift,
+                   void* gscale, void* gshift, int64_t outer, int64_t C, int64_t inner, int pdt, const lsqb200_qargs* q,
+                   void* workspace) {
+    ColSeg cs{};
+    cs.x = x; cs.y = y; cs.g = grad; cs.gx = gx; cs.scale = scale; cs.shift = shift; cs.gscale = gscale; cs.gshift = gshift;
+    if (workspace) {
+        cs.counter = reinterpret_cast<unsigned*>(workspace);
+        cs.acc = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kColAccOffset);
+    }
+    cs.outer = outer; cs.C = C; cs.inner = inner; cs.units_per_row = g.units_per_row; cs.rows_per_split = g.rows_per_split;
+    const double numel = (double)outer * (double)C * (double)inner;
+    cs.gs = q->use_grad_scaling ? q->grad_scaler / std::sqrt(numel * (double)q->quant_max) : q->grad_scaler;
+    cs.qmin = (float)q->quant_min; cs.qmax = (float)q->quant_max; cs.tmin = (float)q->type_min; cs.tmax = (float)q->type_max;
+    cs.tx = g.tx; cs.ty = g.ty; cs.pdt = pdt; cs.sym = q->sym;
+    cs.total_ctas = (unsigned)(g.col_blocks * g.row_splits);
+    return cs;
+}
+
+int launch_col(ColKernelFn k, const ColSeg& cs, const ColGeom& g, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)g.col_blocks, (unsigned)g.row_splits);
+    cfg.blockDim = dim3(kColThreads);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tuning().pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, cs);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return 0;
+}
+
 int forward_common(const void* x, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
                    int64_t inner, int xdt, int pdt, int per_channel, const lsqb200_qargs* q, void* stream) {
     if (int r = check_q(q)) return r;
@@ -107,6 +183,14 @@ int forward_common(const void* x, void* y, const void* scale, const void* shift,
     if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
     if (outer * C * inner == 0) return 0;
     if (!x || !y || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    if (per_channel) {
+        ColKernelFn ck = get_col_fwd_kernel(xdt, mode, q->init_mode != 0, tuning().col_variant);
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, y}), tuning(), occupancy_of((const void*)ck, kColThreads));
+        if (cg.ok) {
+            const ColSeg cs = make_colseg(cg, x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, pdt, q, nullptr);
+            return launch_col(ck, cs, cg, (cudaStream_t)stream);
+        }
+    }
     const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, common_alignment({x, y}), tuning());
     SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
     const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
@@ -134,6 +218,16 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
         return 0;
     }
     if (!grad || !x || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    if (per_channel) {
+        ColKernelFn ck = get_col_bwd_kernel(xdt, mode, bmode_of(q), tuning().col_variant);
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads));
+        if (cg.ok) {
+            if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
+                return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
+            const ColSeg cs = make_colseg(cg, x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, pdt, q, workspace);
+            return launch_col(ck, cs, cg, st);
+        }
+    }
     const Geometry g = plan_geometry(outer, C, inner, xdt, K_BWD, common_alignment({x, grad, gx}), tuning());
     double* partials = nullptr;
     unsigned* counters = nullptr;
@@ -281,6 +375,11 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "max_unit_bytes") g_tuning.max_unit_bytes = v;
         else if (k == "interleave") g_tuning.interleave = v;
         else if (k == "pdl") g_tuning.pdl = v;
+        else if (k == "whole_waves") g_tuning.whole_waves = v;
+        else if (k == "column_path") g_tuning.column_path = v;
+        else if (k == "col_variant") g_tuning.col_variant = (v >= 0 && v < kColVariants) ? v : 0;
+        else if (k == "col_waves") g_tuning.col_waves = v > 0 ? v : 2;
+        else if (k == "column_max_row_bytes") g_tuning.column_max_row_bytes = v;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;
     }

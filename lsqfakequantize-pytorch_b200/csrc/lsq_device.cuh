@@ -227,6 +227,25 @@ __device__ __forceinline__ Chan make_chan(float scale, float shift, const Seg& s
     return c;
 }
 
+// The raw scale / shift loads are issued at kernel entry but the derived constants are formed
+// only after the first data loads of the tile are in flight, so a tile's two dependent DRAM
+// round trips (parameters, then data) overlap instead of adding up.
+template <int MODE>
+struct LazyChan {
+    float sraw, braw;
+    Chan c;
+    bool ready;
+    __device__ __forceinline__ void issue(const Seg& sg, long long pidx) {
+        sraw = load_param(sg.scale, pidx, sg.pdt);
+        braw = load_param(sg.shift, pidx, sg.pdt);
+        ready = false;
+    }
+    __device__ __forceinline__ const Chan& get(const Seg& sg) {
+        if (!ready) { c = make_chan<MODE>(sraw, braw, sg); ready = true; }
+        return c;
+    }
+};
+
 template <int MODE>
 __device__ __forceinline__ float affine_v(float x, const Chan& c) {
     if (MODE == M_HALF_EXACT) return hround(__fadd_rn(hround(__fmul_rn(x, c.inv_s)), c.zp));
@@ -253,9 +272,10 @@ __device__ __forceinline__ float fq_forward(float x, const Chan& c) {
 //     g' * ((xfq - x)*inv_s) and fused into the accumulation (<= 2 ulp per term from the
 //     reference's left-to-right product; only sums are observable and they are held to 1e-6);
 //   * dB = (!mask) * g' is exact, so fma(g', 1 - m, acc) adds exactly the reference's term.
-// ACC is float for the streaming kernels (<= UNROLL*VEC terms per partial, then promoted to
-// double) and double for the warp-group kernels that own short channels.
-template <int MODE, int BMODE, typename ACC>
+// EXACT selects the reference's fp32 terms bit for bit (kernels that own short channels, where
+// few terms are summed and nothing averages the 2-ulp difference out); ACC is the accumulator
+// type (float partials are promoted to double after <= 32-64 terms).
+template <int MODE, int BMODE, bool EXACT, typename ACC>
 __device__ __forceinline__ float fq_backward(float g, float x, const Chan& c, ACC& accS, ACC& accB) {
     const float v = affine_v<MODE>(x, c);
     const bool mask = (v > c.qmin) && (v < c.qmax);
@@ -267,7 +287,7 @@ __device__ __forceinline__ float fq_backward(float g, float x, const Chan& c, AC
         const float d = __fmaf_rn(t, c.s, -x);                     // xfq - x, fused as in the reference build
         const float gg = (BMODE == B_INIT) ? __fmul_rn(2.0f, d) : g;
         const float nm = __fsub_rn(1.0f, m);
-        if (sizeof(ACC) == 4) {
+        if (!EXACT) {
             // streaming kernels: one select + two fused accumulations
             const float w = mask ? __fmul_rn(d, c.inv_s) : t;
             accS = __fmaf_rn(gg, w, accS);
@@ -439,12 +459,13 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
     T* __restrict__ yp = reinterpret_cast<T*>(sg.y);
-    const Chan ch = make_chan<MODE>(load_param(sg.scale, tl.pidx, sg.pdt), load_param(sg.shift, tl.pidx, sg.pdt), sg);
+    LazyChan<MODE> lch;
+    lch.issue(sg, tl.pidx);
 
     if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
-            yp[e] = INIT ? xp[e] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xp[e]), ch));
+            yp[e] = INIT ? xp[e] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xp[e]), lch.get(sg)));
         }
     }
     Walker w;
@@ -463,6 +484,7 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
                 if (INIT) { st_unit<ST, NW>(reinterpret_cast<char*>(yp) + addr[k] * UB, xr[k]); continue; }
+                const Chan& ch = lch.get(sg);
                 float f[VEC];
                 unpack_unit<T, NW>(xr[k], f);
 #pragma unroll
@@ -476,7 +498,7 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
                 if (ok[k]) xr[k] = xp[addr[k]];
 #pragma unroll
             for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) yp[addr[k]] = INIT ? xr[k] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xr[k]), ch));
+                if (ok[k]) yp[addr[k]] = INIT ? xr[k] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xr[k]), lch.get(sg)));
         }
     }
 }
@@ -533,13 +555,14 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const T* __restrict__ gp = reinterpret_cast<const T*>(sg.g);
     T* __restrict__ gxp = reinterpret_cast<T*>(sg.gx);
     const bool write_gx = gxp != nullptr;
-    const Chan ch = make_chan<MODE>(load_param(sg.scale, tl.pidx, sg.pdt), load_param(sg.shift, tl.pidx, sg.pdt), sg);
+    LazyChan<MODE> lch;
+    lch.issue(sg, tl.pidx);
 
     double accS = 0.0, accB = 0.0;
     if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
-            const float dx = fq_backward<MODE, BMODE>(Tr::to_f(gp[e]), Tr::to_f(xp[e]), ch, accS, accB);
+            const float dx = fq_backward<MODE, BMODE, true>(Tr::to_f(gp[e]), Tr::to_f(xp[e]), lch.get(sg), accS, accB);
             if (write_gx) gxp[e] = bmode_passthrough(BMODE) ? gp[e] : Tr::from_f(dx);
         }
     }
@@ -565,11 +588,12 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
+                const Chan& ch = lch.get(sg);
                 float fx[VEC], fg[VEC];
                 unpack_unit<T, NW>(xr[k], fx);
                 unpack_unit<T, NW>(gr[k], fg);
 #pragma unroll
-                for (int e = 0; e < VEC; e++) fg[e] = fq_backward<MODE, BMODE>(fg[e], fx[e], ch, ls, lb);
+                for (int e = 0; e < VEC; e++) fg[e] = fq_backward<MODE, BMODE, G == 32>(fg[e], fx[e], ch, ls, lb);
                 if (write_gx) {
                     if (bmode_passthrough(BMODE)) st_unit<ST, NW>(reinterpret_cast<char*>(gxp) + addr[k] * UB, gr[k]);
                     else st_unit<ST, NW>(reinterpret_cast<char*>(gxp) + addr[k] * UB, pack_unit<T, NW>(fg));
@@ -583,7 +607,7 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
-                const float dx = fq_backward<MODE, BMODE>(Tr::to_f(gr[k]), Tr::to_f(xr[k]), ch, ls, lb);
+                const float dx = fq_backward<MODE, BMODE, G == 32>(Tr::to_f(gr[k]), Tr::to_f(xr[k]), lch.get(sg), ls, lb);
                 if (write_gx) gxp[addr[k]] = bmode_passthrough(BMODE) ? gr[k] : Tr::from_f(dx);
             }
         }

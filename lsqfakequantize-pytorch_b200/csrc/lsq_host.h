@@ -22,7 +22,7 @@ constexpr int kUnrollStats = 4;
 // units in flight per thread and operand: keep ~64 bytes per operand whatever the unit width
 constexpr int unroll_for(int base, int nw) { return nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base; }
 constexpr int kMinBlocksStats = 2;
-constexpr int kMinBlocksFwd = 8;   // __launch_bounds__ min CTAs/SM -> register cap 32
+constexpr int kMinBlocksFwd = 6;   // __launch_bounds__ min CTAs/SM -> register cap 40
 constexpr int kMinBlocksBwd = 4;   // -> register cap 64
 constexpr int kLd = LD_NC_NOALLOC;   // streaming loads: read-only path, no L1 allocation
 constexpr int kSt = ST_DEFAULT;
@@ -45,7 +45,11 @@ KernelFn get_stats_kernel(int xdtype, int nw, int group);
 // Fixed workspace layout (see lsqb200_workspace_bytes): tickets first, partials after.
 constexpr long long kMaxCounters = 4096;     // channels that may be split across tiles
 constexpr long long kMaxSplitTiles = 16384;  // tiles of a split launch (2 doubles each)
-constexpr size_t kWorkspaceBytes = kMaxCounters * 4 + kMaxSplitTiles * 16;
+// third region: [C][2] fp64 accumulators of the column-layout backward; unlike the partials (scratch,
+// always overwritten before being read) this region is ZERO between calls
+constexpr long long kMaxColumnChannels = 16384;
+constexpr size_t kColAccOffset = kMaxCounters * 4 + kMaxSplitTiles * 16;
+constexpr size_t kWorkspaceBytes = kColAccOffset + kMaxColumnChannels * 16;
 
 struct Tuning {
     int sm_count = 148;
@@ -61,6 +65,11 @@ struct Tuning {
     int warp_units = 512;       // tiles with <= this many units go to warp groups
     int min_iters = 1;          // never split below min_iters full group iterations
     int interleave = 1;         // 1: interleave the splits of a channel (grid-stride style), 0: contiguous slices
+    int column_path = 1;        // short channel rows (channels-last, 7x7 / 14x14 maps) use the column-layout kernels
+    int col_variant = 1;        // column kernels: 0 = 128-bit units x2 rows, 1 = x4 rows (default, r1 sweep), 2 = 64-bit units x4 rows, 3 = x8 rows
+    int col_waves = 2;          // column kernels: CTAs = col_waves * sm_count * (resident CTAs/SM of the kernel)
+    int column_max_row_bytes = 512;   // rows shorter than this (or not 16 B multiples) take the column path
+    int whole_waves = 1;        // round big-tensor tile counts to whole waves of resident CTAs
     int pdl = 1;                // launch with programmatic stream serialization (prologue overlaps predecessor's tail)
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
 };
@@ -113,6 +122,15 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
     long long max_splits = g.chan_units / min_units;
     if (max_splits < 1) max_splits = 1;
     if (splits > max_splits) splits = max_splits;
+    // whole waves: when a channel is cut into more tiles than fit on the machine at once, round
+    // the count up to a multiple of the resident CTA slots so the last wave is full
+    if (C == 1) {
+        const long long resident = (long long)tn.sm_count * (kind == K_BWD ? kMinBlocksBwd : (kind == K_FWD ? kMinBlocksFwd : kMinBlocksStats));
+        if (tn.whole_waves && splits > resident) {
+            const long long r = (splits + resident - 1) / resident * resident;
+            if (r <= max_splits) splits = r;
+        }
+    }
     if (kind == K_FWD) {
         // no reduction: nothing limits the split count but launch granularity
     } else {

@@ -110,14 +110,16 @@ def oracle_bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=Fals
 
 
 def assert_grads_close(mine: torch.Tensor, ref: np.ndarray, mag: np.ndarray, rel, what=""):
-    """|mine - ref| <= rel*|ref| + 3e-8*sum|terms| + output rounding.
+    """|mine - ref| <= rel*|ref| + 1e-7*sum|terms| + output rounding.
 
-    The second term is the cancellation floor of the streaming kernels: their per-thread fp32
-    partial sums (<= 32 terms each, then fp64) are good to ~2^-24 of the summed magnitude; the
-    reference's fp32 at::sum is ~10x looser.  Warp-group kernels accumulate in fp64 throughout."""
+    The second term is the fp32 floor shared with the reference: its per-element terms are
+    fp32 (and it rounds term*gs per element, which the oracle reproduces and the kernels - which
+    scale once, in fp64 - deliberately do not), so a sum of n terms carries ~2^-24*sum|t|/sqrt(n)
+    of noise whatever the summation order; the kernels' own accumulation error (fp32 partials of
+    <= 32-64 terms, then fp64) is below that.  The reference's fp32 at::sum is ~10x looser."""
     m = mine.double().cpu().numpy()
     eps_out = {torch.float32: 2.0 ** -24, torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}[mine.dtype]
-    tol = rel * np.abs(ref) + 3e-8 * mag + eps_out * np.abs(ref) + 1e-30
+    tol = rel * np.abs(ref) + 1e-7 * mag + eps_out * np.abs(ref) + 1e-30
     bad = ~(np.abs(m - ref) <= tol)
     bad &= ~(np.isnan(m) & np.isnan(ref))
     assert not bad.any(), (what, m[bad][:5], ref[bad][:5], tol[bad][:5])

@@ -207,6 +207,8 @@ CH_SHAPES = [
     ((256, 64, 1, 1), 0), ((1000, 2048), 0), ((512, 512, 3, 3), 0),
     ((8, 32, 14, 14), 1), ((4, 64, 56, 56), 1), ((16, 1024, 28, 28), 1), ((3, 5, 7), 1), ((3, 5, 7), 2),
     ((32, 1000), 1), ((2, 3, 224, 224), 1), ((64, 256, 7, 7), 1),
+    # short channel rows -> column-layout kernels: channels-last, 7x7 / 14x14 maps, ragged unit/channel overlap
+    ((6272, 1024), 1), ((300, 40), 1), ((64, 2048, 7, 7), 1), ((33, 24, 14, 14), 1), ((5, 12, 2, 3), 1), ((1031, 8), 1),
 ]
 
 
