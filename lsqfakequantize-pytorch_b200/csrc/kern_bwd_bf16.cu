@@ -4,7 +4,7 @@ namespace lsqb200 {
 namespace {
 template <typename T, int MODE, int NW, int G_>
 KernelFn pick_b(int bmode) {
-#define LSQ_B(B_) lsq_bwd_kernel<T, MODE, NW, B_, G_, kThreads, unroll_for(kUnrollBwd, NW), kLd, kSt, kMinBlocksBwd>
+#define LSQ_B(B_) lsq_bwd_kernel<T, MODE, NW, B_, G_, kThreads, unroll_for(kUnrollBwd, NW, G_), kLd, kSt, minb_for(kMinBlocksBwd, G_)>
     switch (bmode) {
         case B_NORMAL: return LSQ_B(B_NORMAL);
         case B_INIT: return LSQ_B(B_INIT);

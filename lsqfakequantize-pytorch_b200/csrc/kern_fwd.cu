@@ -4,7 +4,7 @@ namespace lsqb200 {
 namespace {
 template <typename T, int MODE, int NW>
 KernelFn pick_g(bool init, int group) {
-#define LSQ_F(INIT_, G_) lsq_fwd_kernel<T, MODE, NW, INIT_, G_, kThreads, unroll_for(kUnrollFwd, NW), kLd, kSt, kMinBlocksFwd>
+#define LSQ_F(INIT_, G_) lsq_fwd_kernel<T, MODE, NW, INIT_, G_, kThreads, unroll_for(kUnrollFwd, NW, G_), kLd, kSt, minb_for(kMinBlocksFwd, G_)>
     if (group == 32) return init ? LSQ_F(true, 32) : LSQ_F(false, 32);
     return init ? LSQ_F(true, kThreads) : LSQ_F(false, kThreads);
 #undef LSQ_F

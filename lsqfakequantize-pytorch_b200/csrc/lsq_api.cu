@@ -79,7 +79,8 @@ SegArgs seg_args(const void* x, void* y, const void* g, void* gx, const void* sc
     return a;
 }
 
-int launch(KernelFn k, const Seg& seg, const Seg* table, int nseg, long long tiles, long long grid, cudaStream_t st) {
+int launch(KernelFn k, const Seg& seg, const Seg* table, const int* tile_seg, int nseg, long long tiles, long long grid,
+           cudaStream_t st) {
     if (grid <= 0) return 0;
     if (grid > 2147483647LL) return fail(LSQB200_ERR_ARG, "tensor too large for one launch");
     cudaLaunchConfig_t cfg{};
@@ -92,7 +93,7 @@ int launch(KernelFn k, const Seg& seg, const Seg* table, int nseg, long long til
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = tuning().pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, k, seg, table, nseg, tiles);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, seg, table, tile_seg, nseg, tiles);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     return 0;
 }
@@ -195,7 +196,7 @@ int forward_common(const void* x, void* y, const void* scale, const void* shift,
     SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
     const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
     KernelFn k = get_fwd_kernel(xdt, mode, g.nw, q->init_mode != 0, g.group);
-    return launch(k, seg, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
+    return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
 int backward_common(const void* grad, const void* x, void* gx, const void* scale, const void* shift, void* gscale,
@@ -240,7 +241,7 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
     SegArgs a = seg_args(x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, xdt, pdt, per_channel, q);
     const Seg seg = make_seg(a, g, partials, counters, 0);
     KernelFn k = get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
-    return launch(k, seg, nullptr, 0, g.tiles, g.grid, st);
+    return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, st);
 }
 
 }  // namespace
@@ -253,6 +254,7 @@ struct lsqb200_plan {
         KernelFn kernel = nullptr;
         std::vector<Seg> host;
         Seg* dev = nullptr;
+        int* dev_tile_seg = nullptr;          // tile -> index into `dev`
         long long tiles = 0, grid = 0;
         int group = kThreads;
     };
@@ -315,9 +317,23 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         c.tiles += g.tiles;
     }
     for (auto& c : out) {
-        const long long gpc = kThreads / c.group;
+        const long long gpc = (long long)(kThreads / c.group) * tiles_per_group(c.group);
         c.grid = (c.tiles + gpc - 1) / gpc;
     }
+    return 0;
+}
+
+int upload_tile_map(lsqb200_plan::Class& c) {
+    if (c.dev_tile_seg || c.tiles <= 0 || c.tiles > (1LL << 26)) return 0;   // huge plans keep the in-kernel search
+    std::vector<int> map((size_t)c.tiles);
+    for (size_t i = 0; i < c.host.size(); i++) {
+        const long long b = c.host[i].tile_begin, e = (i + 1 < c.host.size()) ? c.host[i + 1].tile_begin : c.tiles;
+        for (long long t = b; t < e; t++) map[(size_t)t] = (int)i;
+    }
+    cudaError_t e = cudaMalloc(&c.dev_tile_seg, map.size() * sizeof(int));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan tile map)");
+    e = cudaMemcpy(c.dev_tile_seg, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(plan tile map)");
     return 0;
 }
 
@@ -328,6 +344,7 @@ int upload_classes(std::vector<lsqb200_plan::Class>& cls) {
         if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan table)");
         e = cudaMemcpy(c.dev, c.host.data(), c.host.size() * sizeof(Seg), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(plan table)");
+        if (int r = upload_tile_map(c)) return r;
     }
     return 0;
 }
@@ -335,7 +352,7 @@ int upload_classes(std::vector<lsqb200_plan::Class>& cls) {
 int run_classes(std::vector<lsqb200_plan::Class>& cls, cudaStream_t st) {
     for (auto& c : cls) {
         if (c.host.empty()) continue;
-        if (int r = launch(c.kernel, c.host[0], c.dev, (int)c.host.size(), c.tiles, c.grid, st)) return r;
+        if (int r = launch(c.kernel, c.host[0], c.dev, c.dev_tile_seg, (int)c.host.size(), c.tiles, c.grid, st)) return r;
     }
     return 0;
 }
@@ -449,7 +466,7 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
     a.stats_out = scale_out;
     const Seg seg = make_seg(a, g, partials, counters, 0);
     KernelFn k = get_stats_kernel(xdtype, g.nw, g.group);
-    return launch(k, seg, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
+    return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
 int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan** out) {
@@ -513,6 +530,7 @@ int lsqb200_plan_weight_init_stats(lsqb200_plan* plan, float* scale_out, void* s
         if (!c.dev) {
             cudaError_t e = cudaMalloc(&c.dev, c.host.size() * sizeof(Seg));
             if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan table)");
+            if (int r = upload_tile_map(c)) return r;
         }
         cudaError_t e = cudaMemcpyAsync(c.dev, c.host.data(), c.host.size() * sizeof(Seg), cudaMemcpyHostToDevice,
                                         (cudaStream_t)stream);
@@ -532,7 +550,7 @@ int lsqb200_plan_destroy(lsqb200_plan* plan) {
     if (!plan) return 0;
     for (auto* v : {&plan->fwd, &plan->bwd, &plan->stats})
         for (auto& c : *v)
-            if (c.dev) cudaFree(c.dev);
+            { if (c.dev) cudaFree(c.dev); if (c.dev_tile_seg) cudaFree(c.dev_tile_seg); }
     if (plan->workspace) cudaFree(plan->workspace);
     delete plan;
     return 0;

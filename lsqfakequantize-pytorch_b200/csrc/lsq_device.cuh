@@ -335,35 +335,51 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, double* sm /* [
     __syncthreads();   // sm[] may be reused by the caller
 }
 
-// Copy this group's descriptor into shared memory (uniform broadcast reads afterwards).
-// Returns false when the group has no tile (grid round-up).
-template <int G, int THREADS>
-__device__ __forceinline__ bool stage_segment(const Seg& single, const Seg* table, int nseg,
-                                              long long gtile, long long total_tiles, Seg* dst_seg) {
-    // Programmatic dependent launch (sm_90+): let the NEXT kernel of the stream start launching
-    // while this grid drains, and - when this grid itself was launched as a dependent - wait
-    // for the previous grid to complete before touching any global memory.  Both are no-ops
-    // for ordinary launches.
+// Programmatic dependent launch (sm_90+): let the NEXT kernel of the stream start launching while
+// this grid drains, and - when this grid itself was launched as a dependent - wait for the
+// previous grid to complete before touching any global memory.  No-ops for ordinary launches.
+__device__ __forceinline__ void pdl_prologue() {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (gtile >= total_tiles) return false;      // whole group exits together (G == THREADS: never)
+}
+
+// A group may walk several CONSECUTIVE tiles (rows of the same weight tensor, as a rule), so
+// the descriptor look-up and staging are paid once per few rows, not once per row.
+__host__ __device__ constexpr int tiles_per_group(int group) { return (void)group, 1; }   // r1: 4 rows per warp measured slower (fewer CTAs in flight); kept as a knob
+
+// Copy the tile's descriptor into shared memory (uniform broadcast reads afterwards) unless the
+// group already holds it (`staged` = index of the staged segment, -1 = the single descriptor).
+template <int G, int THREADS>
+__device__ __forceinline__ void stage_segment(const Seg& single, const Seg* table, const int* tile_seg, int nseg,
+                                              long long gtile, Seg* dst_seg, int& staged) {
+    int want = -1;
+    if (table != nullptr) {
+        if (tile_seg != nullptr) {
+            want = tile_seg[gtile];               // plan-time lookup: one load instead of a dependent search
+        } else {
+            int lo = 0, hi = nseg - 1;            // last segment with tile_begin <= gtile
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (table[mid].tile_begin <= gtile) lo = mid; else hi = mid - 1;
+            }
+            want = lo;
+        }
+    }
+    if (want == staged) return;                   // uniform across the group
     const int tg = threadIdx.x % G;
     uint32_t* dst = reinterpret_cast<uint32_t*>(dst_seg);
     constexpr int NW = sizeof(Seg) / 4;
-    if (table == nullptr) {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&single);
-        for (int i = tg; i < NW; i += G) dst[i] = src[i];
-    } else {
-        int lo = 0, hi = nseg - 1;                // last segment with tile_begin <= gtile
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (table[mid].tile_begin <= gtile) lo = mid; else hi = mid - 1;
-        }
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&table[lo]);
-        for (int i = tg; i < NW; i += G) dst[i] = src[i];
-    }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(want < 0 ? &single : &table[want]);
+    if (staged != -2) group_sync<G, THREADS>();   // readers of the previous descriptor are done
+    for (int i = tg; i < NW; i += G) dst[i] = src[i];
     group_sync<G, THREADS>();
-    return true;
+    staged = want;
+}
+
+// 64-bit division costs ~100 instructions; operands almost always fit 32 bits (uniform branch)
+__device__ __forceinline__ long long fast_div(long long a, long long b) {
+    if ((((unsigned long long)a | (unsigned long long)b) >> 32) == 0) return (long long)((unsigned)a / (unsigned)b);
+    return a / b;
 }
 
 // Walks the units [u0, u1) of one channel slice, G threads interleaved, yielding unit addresses.
@@ -382,10 +398,15 @@ struct Walker {
         vpr = (int)sg.vpr; row_stride = sg.row_stride; base = base_unit;
         const long long u = u0 + tg;
         const long long step = sg.interleave ? (long long)sg.splits * G : (long long)G;
-        left = (u < u1) ? (unsigned)((u1 - u + step - 1) / step) : 0u;
-        const long long nn = u / vpr;
-        n = (int)nn; col = (int)(u - nn * vpr);
-        dn = (int)(step / vpr); dcol = (int)(step - (long long)dn * vpr);
+        left = (u < u1) ? (unsigned)fast_div(u1 - u + step - 1, step) : 0u;
+        if (sg.regime == 0) {                       // artificial rows of 2^30 units: shifts, no division
+            n = (int)(u >> 30); col = (int)(u & ((1LL << 30) - 1));
+            dn = (int)(step >> 30); dcol = (int)(step & ((1LL << 30) - 1));
+        } else {
+            const long long nn = fast_div(u, vpr);
+            n = (int)nn; col = (int)(u - nn * vpr);
+            dn = (int)fast_div(step, vpr); dcol = (int)(step - (long long)dn * vpr);
+        }
     }
     __device__ __forceinline__ bool more() const { return left != 0u; }
     __device__ __forceinline__ bool next(long long& addr) {
@@ -408,8 +429,8 @@ template <int VEC>
 __device__ __forceinline__ TileCtx make_tile(const Seg& sg, long long gtile) {
     TileCtx t;
     t.ltile = gtile - sg.tile_begin;
-    t.c = t.ltile / sg.splits;
-    t.j = (int)(t.ltile - t.c * sg.splits);
+    if (sg.splits == 1) { t.c = t.ltile; t.j = 0; }
+    else { t.c = fast_div(t.ltile, sg.splits); t.j = (int)(t.ltile - t.c * sg.splits); }
     t.pidx = sg.per_channel ? t.c : 0;
     long long chan_units = sg.chan_units;
     t.peel_n0 = t.peel_n1 = 0; t.peel_begin0 = t.peel_begin1 = 0;
@@ -446,15 +467,21 @@ __device__ __forceinline__ TileCtx make_tile(const Seg& sg, long long gtile) {
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int NW, bool INIT, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
-lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
+lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                long long total_tiles) {
     using Tr = ElemTraits<T>;
     constexpr int VEC = UnitOf<T, NW>::VEC;
     constexpr int UB = NW * 4;   // unit bytes
     constexpr int GROUPS = THREADS / G;
     __shared__ Seg smem_seg[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
-    const long long gtile = (long long)blockIdx.x * GROUPS + grp;
-    if (!stage_segment<G, THREADS>(single, table, nseg, gtile, total_tiles, &smem_seg[grp])) return;
+    constexpr int ROWS = tiles_per_group(G);
+    pdl_prologue();
+    int staged = -2;
+    for (int row_i = 0; row_i < ROWS; row_i++) {
+    const long long gtile = ((long long)blockIdx.x * GROUPS + grp) * ROWS + row_i;
+    if (gtile >= total_tiles) break;              // whole group leaves together
+    stage_segment<G, THREADS>(single, table, tile_seg, nseg, gtile, &smem_seg[grp], staged);
     const Seg& sg = smem_seg[grp];
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
@@ -501,6 +528,7 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
                 if (ok[k]) yp[addr[k]] = INIT ? xr[k] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xr[k]), lch.get(sg)));
         }
     }
+    }   // tiles of this group
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -538,7 +566,8 @@ __device__ __forceinline__ bool channel_finish(const Seg& sg, const TileCtx& tl,
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int NW, int BMODE, int G, int THREADS, int UNROLL, int LD, int ST, int MINB = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
-lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
+lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                long long total_tiles) {
     using Tr = ElemTraits<T>;
     constexpr int VEC = UnitOf<T, NW>::VEC;
     constexpr int UB = NW * 4;   // unit bytes
@@ -547,8 +576,13 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     __shared__ double red[64];
     __shared__ int last_flag[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
-    const long long gtile = (long long)blockIdx.x * GROUPS + grp;
-    if (!stage_segment<G, THREADS>(single, table, nseg, gtile, total_tiles, &smem_seg[grp])) return;
+    constexpr int ROWS = tiles_per_group(G);
+    pdl_prologue();
+    int staged = -2;
+    for (int row_i = 0; row_i < ROWS; row_i++) {
+    const long long gtile = ((long long)blockIdx.x * GROUPS + grp) * ROWS + row_i;
+    if (gtile >= total_tiles) break;              // whole group leaves together
+    stage_segment<G, THREADS>(single, table, tile_seg, nseg, gtile, &smem_seg[grp], staged);
     const Seg& sg = smem_seg[grp];
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
@@ -619,13 +653,14 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
             store_param(sg.gscale, tl.pidx, sg.pdt, 0.0);
             store_param(sg.gshift, tl.pidx, sg.pdt, 0.0);
         }
-        return;
+        continue;
     }
-    if (!channel_finish<G, THREADS>(sg, tl, accS, accB, red, &last_flag[grp], tg)) return;
+    if (!channel_finish<G, THREADS>(sg, tl, accS, accB, red, &last_flag[grp], tg)) continue;
     if (tg == 0) {
         store_param(sg.gscale, tl.pidx, sg.pdt, accS * sg.gs);
         store_param(sg.gshift, tl.pidx, sg.pdt, sg.sym ? 0.0 : accB * sg.gs);
     }
+    }   // tiles of this group
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -634,7 +669,8 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
 // ---------------------------------------------------------------------------------------------
 template <typename T, int NW, int G, int THREADS, int UNROLL, int LD, int MINB = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
-lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, int nseg, long long total_tiles) {
+lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                long long total_tiles) {
     using Tr = ElemTraits<T>;
     constexpr int VEC = UnitOf<T, NW>::VEC;
     constexpr int UB = NW * 4;   // unit bytes
@@ -643,19 +679,26 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
     __shared__ double red[64];
     __shared__ int last_flag[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
-    const long long gtile = (long long)blockIdx.x * GROUPS + grp;
-    if (!stage_segment<G, THREADS>(single, table, nseg, gtile, total_tiles, &smem_seg[grp])) return;
+    constexpr int ROWS = tiles_per_group(G);
+    pdl_prologue();
+    int staged = -2;
+    for (int row_i = 0; row_i < ROWS; row_i++) {
+    const long long gtile = ((long long)blockIdx.x * GROUPS + grp) * ROWS + row_i;
+    if (gtile >= total_tiles) break;              // whole group leaves together
+    stage_segment<G, THREADS>(single, table, tile_seg, nseg, gtile, &smem_seg[grp], staged);
     const Seg& sg = smem_seg[grp];
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
-    const double pivot = (double)Tr::to_f(xp[tl.c * sg.inner]);      // element (0, c, 0)
+    const float pivot = Tr::to_f(xp[tl.c * sg.inner]);      // element (0, c, 0): shift that keeps the sums small
 
+    // per unit: d = w - pivot, sum d and sum d^2 over the unit's <= 16 elements in fp32 (FADD / FFMA),
+    // then one promotion to fp64 per unit - the fp64 pipe sees 2 adds per unit instead of 4 ops per element
     double s1 = 0.0, s2 = 0.0;
     if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
-            const double d = (double)Tr::to_f(xp[e]) - pivot;
-            s1 += d; s2 = fma(d, d, s2);
+            const float d = __fsub_rn(Tr::to_f(xp[e]), pivot);
+            s1 += (double)d; s2 += (double)__fmul_rn(d, d);
         }
     }
     Walker w;
@@ -669,31 +712,33 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
             Raw<NW> xr[UNROLL];
 #pragma unroll
             for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + addr[k] * UB);
+                xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + (ok[k] ? addr[k] : addr[0]) * UB);
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
                 float f[VEC];
                 unpack_unit<T, NW>(xr[k], f);
+                float u1 = 0.f, u2 = 0.f;
 #pragma unroll
                 for (int e = 0; e < VEC; e++) {
-                    const double d = (double)f[e] - pivot;
-                    s1 += d; s2 = fma(d, d, s2);
+                    const float d = __fsub_rn(f[e], pivot);
+                    u1 = __fadd_rn(u1, d); u2 = __fmaf_rn(d, d, u2);
                 }
+                s1 += (double)u1; s2 += (double)u2;
             }
         } else {
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
-                const double d = (double)Tr::to_f(xp[addr[k]]) - pivot;
-                s1 += d; s2 = fma(d, d, s2);
+                const float d = __fsub_rn(Tr::to_f(xp[addr[k]]), pivot);
+                s1 += (double)d; s2 += (double)__fmul_rn(d, d);
             }
         }
     }
-    if (!channel_finish<G, THREADS>(sg, tl, s1, s2, red, &last_flag[grp], tg)) return;
+    if (!channel_finish<G, THREADS>(sg, tl, s1, s2, red, &last_flag[grp], tg)) continue;
     if (tg == 0) {
         const double K = (double)sg.chan_elems;
-        const double mean = pivot + s1 / K;
+        const double mean = (double)pivot + s1 / K;
         double var = (s2 - s1 * s1 / K) / (K - 1.0);               // unbiased (torch.std default); K == 1 -> NaN
         if (var < 0.0) var = 0.0;
         const float mu = (float)mean, sd = (float)sqrt(var);
@@ -701,6 +746,7 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
         const float hi = fabsf(__fadd_rn(mu, __fmul_rn(3.0f, sd)));
         sg.stats_out[tl.c] = __fdiv_rn(fmaxf(lo, hi), sg.stats_denom);
     }
+    }   // tiles of this group
 }
 
 }  // namespace lsqb200

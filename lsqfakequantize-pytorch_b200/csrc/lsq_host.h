@@ -20,14 +20,18 @@ constexpr int kUnrollFwd = 2;
 constexpr int kUnrollBwd = 2;
 constexpr int kUnrollStats = 4;
 // units in flight per thread and operand: keep ~64 bytes per operand whatever the unit width
-constexpr int unroll_for(int base, int nw) { return nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base; }
+// warp groups own short rows and have little else to overlap their latency with: twice the units in flight
+constexpr int unroll_for(int base, int nw, int group = 256) {
+    return (nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base) * (group == 32 ? 2 : 1);
+}
 constexpr int kMinBlocksStats = 2;
+constexpr int minb_for(int base, int group) { return group == 32 ? (base * 2 / 3 > 0 ? base * 2 / 3 : 1) : base; }
 constexpr int kMinBlocksFwd = 6;   // __launch_bounds__ min CTAs/SM -> register cap 40
 constexpr int kMinBlocksBwd = 4;   // -> register cap 64
 constexpr int kLd = LD_NC_NOALLOC;   // streaming loads: read-only path, no L1 allocation
 constexpr int kSt = ST_DEFAULT;
 
-using KernelFn = void (*)(const Seg, const Seg*, int, long long);
+using KernelFn = void (*)(const Seg, const Seg*, const int*, int, long long);
 // defined in kern_fwd.cu / kern_bwd_*.cu / kern_stats.cu (one translation unit per family so they build in parallel)
 KernelFn get_fwd_kernel(int xdtype, int mode, int nw, bool init, int group);
 KernelFn get_bwd_kernel_f32(int mode, int nw, int bmode, int group);
@@ -62,7 +66,7 @@ struct Tuning {
     int stats_tile_kb = 128;
     int fwd_min_tiles_per_sm = 16;   // small tensors: shrink tiles until the machine is full
     int bwd_min_tiles_per_sm = 8;
-    int warp_units = 512;       // tiles with <= this many units go to warp groups
+    int warp_units = 1024;      // channels with <= this many units are owned by warp groups (all ResNet-50 weight rows)
     int min_iters = 1;          // never split below min_iters full group iterations
     int interleave = 1;         // 1: interleave the splits of a channel (grid-stride style), 0: contiguous slices
     int column_path = 1;        // short channel rows (channels-last, 7x7 / 14x14 maps) use the column-layout kernels
@@ -153,7 +157,7 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
     g.interleave = (tn.interleave && splits > 1) ? 1 : 0;
     g.splits = (int)splits;
     g.tiles = C * splits;
-    const long long gpc = threads / g.group;
+    const long long gpc = (long long)(threads / g.group) * tiles_per_group(g.group);
     g.grid = (g.tiles + gpc - 1) / gpc;
     return g;
 }

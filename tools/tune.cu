@@ -146,7 +146,7 @@ int main(int argc, char** argv) {
             for (int r = 0; r < reps + 2; r++) {
                 CK(cudaMemsetAsync(flush, r, flush_bytes));   // defeat L2 between iterations
                 CK(cudaEventRecord(e0));
-                v.fn<<<(unsigned)geo.grid, v.threads>>>(seg, nullptr, 0, geo.tiles);
+                v.fn<<<(unsigned)geo.grid, v.threads>>>(seg, nullptr, nullptr, 0, geo.tiles);
                 CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
                 CK(cudaGetLastError());
                 float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
