@@ -336,6 +336,39 @@ def run_b200(args):
     bwd_ms = statistics.mean(a.elapsed_time(b) for a, b in bw)
     achieved = bwd_bytes / (bwd_ms * 1e-3) / 1e9
 
+    # ---- same step with ALL activation sites in one multi-tensor launch per direction: what is left when the
+    #      per-launch ramp / tail (the difference between the per-site step and the kernels' own rate) is gone
+    plan_mode = None
+    if aplan is None and not args.no_plan_mode:
+        asites = []
+        for a in acts:
+            gs_, gb_ = flat.views(a["name"])
+            asites.append(Site(x=a["x"], y=a["y"], grad=a["g"], gx=a["gx"], scale=a["s"], shift=a["b"], gscale=gs_, gshift=gb_,
+                               quant_min=0, quant_max=127, type_min=0, type_max=255))
+        p2 = LSQPlan(asites)
+
+        def step2():
+            p2.forward(); wplan.forward(); p2.backward(); wplan.backward()
+            if world > 1:
+                flat.all_reduce()
+        for _ in range(3):
+            step2()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(args.steps):
+            step2()
+        p1.record(stream)
+        barrier()
+        tp = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        pms = tp.item() / args.steps
+        plan_mode = {"value": round(alg_bytes_rank * world / (pms * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(pms, 4),
+                     "launches_per_step": p2.launches(False) + p2.launches(True) + wplan.launches(False) + wplan.launches(True),
+                     "note": "torchlsq.multi.LSQPlan: all 71 activation sites in one launch per direction"}
+        p2.close()
+
     # ---- mu +- 3 sigma init throughput (one launch over all 54 weights)
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
@@ -379,9 +412,10 @@ def run_b200(args):
         line = {
             "metric": "lsq_fwd_bwd_algorithmic_GBps", "value": round(value, 1), "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 math on bf16 activations + f32 weights", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "resnet50_qat_fakequant: BASELINE configs[4] per-rank shard (71 bf16 per-tensor activation sites "
                                    "+ 54 fp32 per-channel weights, fwd+bwd, flat-grad all-reduce when N>1)",
+                       "storage": "bf16 activations, f32 weights and parameters; arithmetic in f32, reductions in f64",
                        "batch_per_gpu": B, "global_batch": B * world, "elements_per_gpu_step": n_act + n_w,
                        "algorithmic_bytes_per_gpu_step": alg_bytes_rank,
                        "l2": "every site has its own x/y/g/gx buffers (%.1f GB resident) - far larger than the 126 MB L2, no flush needed" % (4 * 2 * n_act / 1e9),
@@ -394,7 +428,7 @@ def run_b200(args):
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": bwd_bytes, "avg_ms_per_step": round(bwd_ms, 4)},
-            "weight_init_stats_GBps": round(init_gbps, 1),
+            "plan_mode": plan_mode, "weight_init_stats_GBps": round(init_gbps, 1),
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(),
         }
@@ -407,19 +441,24 @@ def run_b200(args):
 
 def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
     """Host buffers -> public op (torchlsq.functional.lsq + autograd) -> host buffers.
-    Two lanes (streams) so one site's copies overlap the other's kernels; staging buffers are
-    sized for the largest site and reused (the bytes moved per step are the full workload's)."""
+
+    Three-stage pipeline over the 71 activation sites: a copy-in stream (pinned x, g -> device), the
+    compute stream (the public op's forward and autograd backward) and a copy-out stream (y, grad_x ->
+    pinned host), chained with events over a ring of device buffer sets, so both PCIe directions stay
+    busy while the kernels run.  Staging buffers are sized for the largest site and reused; the bytes
+    moved per step are the full workload's.  Weights live on the device (as in training); their
+    gradients and every site's grad_scale / grad_shift are read back."""
     steps = max(1, min(args.steps, args.e2e_steps))
     nmax = B * max(math.prod(s) for s in ACT_SHAPES)
-    lanes = []
-    for _ in range(2):
-        lanes.append(dict(stream=torch.cuda.Stream(dev),
-                          xh=torch.empty(nmax, dtype=torch.bfloat16).pin_memory().normal_().relu_(),
-                          gh=torch.empty(nmax, dtype=torch.bfloat16).pin_memory().normal_(),
-                          yh=torch.empty(nmax, dtype=torch.bfloat16).pin_memory(),
-                          gxh=torch.empty(nmax, dtype=torch.bfloat16).pin_memory(),
-                          xd=torch.empty(nmax, dtype=torch.bfloat16, device=dev),
-                          gd=torch.empty(nmax, dtype=torch.bfloat16, device=dev)))
+    NB = 3
+    s_in, s_cmp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    xh = torch.empty(nmax, dtype=torch.bfloat16).pin_memory().normal_().relu_()
+    gh = torch.empty(nmax, dtype=torch.bfloat16).pin_memory().normal_()
+    yh = torch.empty(nmax, dtype=torch.bfloat16).pin_memory()
+    gxh = torch.empty(nmax, dtype=torch.bfloat16).pin_memory()
+    ring = [dict(xd=torch.empty(nmax, dtype=torch.bfloat16, device=dev), gd=torch.empty(nmax, dtype=torch.bfloat16, device=dev),
+                 yd=None, gxd=None, in_done=torch.cuda.Event(), cmp_done=torch.cuda.Event(), out_done=torch.cuda.Event())
+            for _ in range(NB)]
     grads_h = torch.empty(flat.numel, dtype=torch.float32).pin_memory()
     s_act = torch.tensor([0.03], device=dev, requires_grad=True)
     b_act = torch.tensor([0.0], device=dev, requires_grad=True)
@@ -428,21 +467,31 @@ def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
     sizes = [B * math.prod(s) for s in ACT_SHAPES]
     h2d = sum(2 * 2 * n for n in sizes)
     d2h = sum(2 * 2 * n for n in sizes) + 4 * flat.numel
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 
     def one_step():
         for i, n in enumerate(sizes):
-            ln = lanes[i & 1]
-            with torch.cuda.stream(ln["stream"]):
-                xd = ln["xd"][:n]
-                gd = ln["gd"][:n]
-                xd.copy_(ln["xh"][:n], non_blocking=True)
-                gd.copy_(ln["gh"][:n], non_blocking=True)
-                xl = xd.detach().requires_grad_(True)
+            slot = ring[i % NB]
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(slot["cmp_done"])            # the buffers' previous kernels are done
+                slot["xd"][:n].copy_(xh[:n], non_blocking=True)
+                slot["gd"][:n].copy_(gh[:n], non_blocking=True)
+                slot["in_done"].record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(slot["in_done"])
+                s_cmp.wait_event(slot["out_done"])           # previous outputs of this slot have left the device
+                xl = slot["xd"][:n].detach().requires_grad_(True)
                 y = lsq(xl, s_act, b_act, 0, 127, 0, 255)
-                y.backward(gd)
-                ln["yh"][:n].copy_(y.detach(), non_blocking=True)
-                ln["gxh"][:n].copy_(xl.grad, non_blocking=True)
-        with torch.cuda.stream(lanes[0]["stream"]):
+                y.backward(slot["gd"][:n])
+                slot["yd"], slot["gxd"] = y.detach(), xl.grad
+                slot["cmp_done"].record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(slot["cmp_done"])
+                yh[:n].copy_(slot["yd"], non_blocking=True)
+                gxh[:n].copy_(slot["gxd"], non_blocking=True)
+                slot["yd"].record_stream(s_out); slot["gxd"].record_stream(s_out)
+                slot["out_done"].record(s_out)
+        with torch.cuda.stream(s_cmp):
             for w, s, b, g in w_leaf:
                 yw = lsq(w, s, b, -128, 127, -128, 127, axis=0, is_affine=False, is_perchannel=True)
                 yw.backward(g)
@@ -451,8 +500,9 @@ def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
             for w, s, b, _ in w_leaf:
                 w.grad = s.grad = b.grad = None
             s_act.grad = b_act.grad = None
-        for ln in lanes:
-            torch.cuda.current_stream(dev).wait_stream(ln["stream"])
+        cur = torch.cuda.current_stream(dev)
+        for st in (s_in, s_cmp, s_out):
+            cur.wait_stream(st)
 
     def barrier():
         if world > 1:
@@ -473,8 +523,8 @@ def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
     n_w = sum(math.prod(s) for s in W_SHAPES)
     alg = (5 * 2 * sum(sizes) + 5 * 4 * n_w) * world
     return {"value": round(alg / dt / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "steps": steps, "ms_per_step": round(dt * 1e3, 2),
-            "path": "pinned host x,g -> torchlsq.functional.lsq + autograd on 2 streams -> pinned host y,gx,grads; weights stay on device"}
+            "steps": steps, "ms_per_step": round(dt * 1e3, 2), "pcie_GBps_each_way": round(h2d / dt / 1e9, 1),
+            "path": "pinned host x,g -> torchlsq.functional.lsq + autograd (copy-in / compute / copy-out streams) -> pinned host y,gx,grads; weights stay on device"}
 
 
 def main():
@@ -487,6 +537,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2, help="images per activation site in the CPU reference sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-plan-mode", action="store_true", help="skip the extra multi-tensor-plan measurement")
     ap.add_argument("--plan-activations", action="store_true", help="run all activation sites through one multi-tensor plan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

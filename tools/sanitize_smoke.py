@@ -1,0 +1,42 @@
+"""Small run of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck / synccheck).
+Sizes are tiny so the 10-50x slowdown stays in seconds; results are still checked against the oracle."""
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, 'lsqfakequantize-pytorch_b200'); sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import gpu_util as U
+from torchlsq.multi import LSQPlan, Site
+
+def check(x, g, s, b, q, outer=1, C=1, inner=None, pc=False):
+    y = U.fwd(x, s, b, q, outer, C, inner, pc)
+    assert U.same_bits(y, U.oracle_fwd(x, s, b, q, outer, C, inner, pc))
+    gx, gs, gb = U.bwd(g, x, s, b, q, outer, C, inner, pc)
+    ogx, ogs, ogb, ms, mb = U.oracle_bwd(g, x, s, b, q, outer, C, inner, pc)
+    assert U.same_bits(gx, ogx)
+    U.assert_grads_close(gs, ogs, ms, 1e-5); U.assert_grads_close(gb, ogb, mb, 1e-5)
+
+gen = torch.Generator().manual_seed(0)
+for dt in (torch.float32, torch.bfloat16, torch.float16):
+    for n in (5, 4099, 300_001):                       # scalar tail, single tile, split tiles + last-arriver reduce
+        x = torch.randn(n, generator=gen).to(dt).to(U.DEV); g = torch.randn(n, generator=gen).to(dt).to(U.DEV)
+        s = torch.tensor([0.03], device=U.DEV); b = torch.tensor([-1.7], device=U.DEV)
+        for mode in (dict(), dict(init_mode=True), dict(eval_mode=True)):
+            check(x, g, s, b, U.qa(**mode))
+    for shape, axis in (((6, 4, 3, 3), 0), ((64, 3, 7, 7), 0), ((4, 32, 14, 14), 1), ((2, 16, 56, 56), 1), ((64, 40), 1), ((16, 64, 7, 7), 1), ((3, 5, 7), 2)):
+        n = int(np.prod(shape)); outer = int(np.prod(shape[:axis])); C = shape[axis]; inner = n // (outer * C)
+        x = torch.randn(n, generator=gen).to(dt).to(U.DEV); g = torch.randn(n, generator=gen).to(dt).to(U.DEV)
+        s = (0.02 + 0.02 * torch.rand(C, generator=gen)).to(U.DEV); b = (-torch.rand(C, generator=gen)).to(U.DEV)
+        check(x, g, s, b, U.qa(), outer, C, inner, True)
+xh = torch.randn(20_001, generator=gen).half().to(U.DEV); gh = torch.randn(20_001, generator=gen).half().to(U.DEV)
+check(xh, gh, torch.tensor([0.03], device=U.DEV).half(), torch.tensor([-1.7], device=U.DEV).half(), U.qa(use_gs=False))
+sites = []
+for shp in ((16, 3, 7, 7), (32, 16, 1, 1), (8, 8, 3, 3)):
+    w = (torch.randn(*shp, generator=gen) * 0.05).to(U.DEV)
+    sites.append(Site(x=w, y=torch.empty_like(w), grad=torch.randn(*shp, generator=gen).to(U.DEV), gx=torch.empty_like(w),
+                      scale=torch.full((shp[0],), 0.002, device=U.DEV), shift=torch.zeros(shp[0], device=U.DEV),
+                      gscale=torch.empty(shp[0], device=U.DEV), gshift=torch.empty(shp[0], device=U.DEV),
+                      quant_min=-128, quant_max=127, type_min=-128, type_max=127, axis=0, is_affine=False, is_perchannel=True))
+plan = LSQPlan(sites); plan.forward(); plan.backward(); out = plan.weight_init_stats()
+torch.cuda.synchronize()
+assert torch.isfinite(out).all()
+print("sanitize_smoke ok")
