@@ -105,6 +105,25 @@ LSQB200_API int lsqb200_weight_init_stats(const void* w, float* scale_out,
                               int64_t quant_min, int64_t quant_max,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- fused observer step (the module's default `init_mode='observer'`): replaces, for one forward,
+ *      `self.activation_post_process(x)` + `calculate_qparams()` + `_set_weights(scale, zero_point)`,
+ *      quantized/modules/observers.py:446-449 with torch's MinMaxObserver / MovingAverageMinMaxObserver
+ *      (and their PerChannel variants).  One read of x, no host sync, no fp32 copy of x.
+ *      min_val / max_val: running state, float[C] or [1], updated in place (+inf / -inf = never observed);
+ *      scale_out / shift_out (may be NULL): the LSQ parameters, shift = -zero_point * scale. ---------- */
+typedef struct lsqb200_observer_args {
+    int64_t quant_min, quant_max;   /* the observer's range (after reduce_range) */
+    double averaging_constant;      /* EMA constant; ignored unless moving_average */
+    double eps;                     /* lower bound of scale (observer.eps) */
+    int32_t moving_average;         /* 0: running min / max, 1: exponential moving average */
+    int32_t symmetric;              /* per_tensor_symmetric / per_channel_symmetric */
+    int32_t zero_point_sym;         /* zero point of the symmetric scheme: 0 (qint8), 128 or (qmin+qmax)//2 (quint8) */
+    int32_t reserved;
+} lsqb200_observer_args;
+LSQB200_API int lsqb200_observe(const void* x, int64_t outer, int64_t C, int64_t inner, int xdtype, int per_channel,
+                    float* min_val, float* max_val, float* scale_out, float* shift_out,
+                    const lsqb200_observer_args* args, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- multi-tensor plans: one launch for many fake-quant sites (the 54 ResNet-50 weights, or
  *      every site of a step).  Semantics per segment are exactly those of the calls above. --- */
 typedef struct lsqb200_segment {

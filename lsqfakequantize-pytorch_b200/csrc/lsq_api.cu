@@ -469,6 +469,38 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
+int lsqb200_observe(const void* x, int64_t outer, int64_t C, int64_t inner, int xdtype, int per_channel, float* min_val,
+                    float* max_val, float* scale_out, float* shift_out, const lsqb200_observer_args* oa, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    if (!oa) return fail(LSQB200_ERR_ARG, "observer args are NULL");
+    if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
+    if (xdtype < 0 || xdtype > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    if (oa->quant_min >= oa->quant_max) return fail(LSQB200_ERR_ARG, "quant_min must be smaller than quant_max");
+    if (outer * C * inner == 0) return 0;                       // torch observers ignore empty inputs too
+    if (!x || !min_val || !max_val) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    if (!per_channel) { inner *= outer * C; outer = 1; C = 1; }
+    const Geometry g = plan_geometry(outer, C, inner, xdtype, K_STATS, common_alignment({x}), tuning());
+    double* partials = nullptr;
+    unsigned* counters = nullptr;
+    if (g.splits > 1) {
+        if (!workspace || workspace_bytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
+            return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
+        counters = reinterpret_cast<unsigned*>(workspace);
+        partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kMaxCounters * 4);
+    }
+    lsqb200_qargs q{};
+    q.quant_min = oa->quant_min; q.quant_max = oa->quant_max; q.type_min = oa->quant_min; q.type_max = oa->quant_max; q.grad_scaler = 1.0;
+    SegArgs a = seg_args(x, scale_out, nullptr, shift_out, nullptr, nullptr, min_val, max_val, outer, C, inner, xdtype, DT_F32,
+                         per_channel ? 1 : 0, &q);
+    Seg seg = make_seg(a, g, partials, counters, 0);
+    seg.obs_c = (float)oa->averaging_constant;
+    seg.obs_eps = (float)oa->eps;
+    seg.obs_flags = (oa->symmetric ? 1 : 0) | (oa->moving_average ? 2 : 0);
+    seg.obs_zp_sym = oa->zero_point_sym;
+    KernelFn k = get_observe_kernel(xdtype, g.nw, g.group);
+    return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
+}
+
 int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan** out) {
     if (!segs || nseg <= 0 || !out) return fail(LSQB200_ERR_PLAN, "empty segment list");
     lsqb200_plan* p = new lsqb200_plan();

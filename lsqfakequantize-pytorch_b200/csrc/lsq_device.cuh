@@ -71,6 +71,10 @@ struct Seg {
     int vec;               // elements per unit actually used
     int interleave;        // 1: splits of a channel are interleaved at group granularity
     int group;             // threads per tile-owning group (32 or THREADS)
+    // observer step (lsq_observe_kernel): x -> running min/max (gscale/gshift slots hold float* state) -> scale/shift
+    float obs_c, obs_eps;  // averaging constant, eps
+    int obs_flags;         // bit 0: symmetric qscheme, bit 1: moving average (else running extrema)
+    int obs_zp_sym;        // zero point of the symmetric scheme (0, 128 or (qmin+qmax)//2)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -747,6 +751,172 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
         sg.stats_out[tl.c] = __fdiv_rn(fmaxf(lo, hi), sg.stats_denom);
     }
     }   // tiles of this group
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Observer step (init_mode='observer', observers.py:446-449): ONE read of x gives the per-tensor /
+// per-channel min and max; the last tile of a channel then does, on the device and with the same
+// fp32 operations in the same order, what torch's observers and the module do on the host:
+//   MinMaxObserver / MovingAverage(PerChannel)MinMaxObserver.forward   (running extrema or EMA)
+//   UniformQuantizationObserverBase._calculate_qparams                 (scale, zero_point)
+//   LSQFakeQuantizer._set_weights                                      (scale, shift = -zp * scale)
+// NaN propagates like torch.aminmax (min.NaN / max.NaN).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float nan_min(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float nan_max(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+template <typename T, int NW, int G, int THREADS, int UNROLL, int LD, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_observe_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                long long total_tiles) {
+    using Tr = ElemTraits<T>;
+    constexpr int VEC = UnitOf<T, NW>::VEC;
+    constexpr int UB = NW * 4;   // unit bytes
+    constexpr int GROUPS = THREADS / G;
+    __shared__ Seg smem_seg[GROUPS];
+    __shared__ float red[64];
+    __shared__ int last_flag[GROUPS];
+    const int grp = threadIdx.x / G, tg = threadIdx.x % G;
+    pdl_prologue();
+    int staged = -2;
+    const long long gtile = (long long)blockIdx.x * GROUPS + grp;
+    if (gtile >= total_tiles) return;
+    stage_segment<G, THREADS>(single, table, tile_seg, nseg, gtile, &smem_seg[grp], staged);
+    const Seg& sg = smem_seg[grp];
+    const TileCtx tl = make_tile<VEC>(sg, gtile);
+    const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+    if constexpr (VEC > 1) {
+        for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
+            const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
+            const float v = Tr::to_f(xp[e]);
+            mn = nan_min(mn, v); mx = nan_max(mx, v);
+        }
+    }
+    Walker w;
+    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    while (w.more()) {
+        long long addr[UNROLL];
+        bool ok[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
+        if constexpr (VEC > 1) {
+            Raw<NW> xr[UNROLL];
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)
+                xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + (ok[k] ? addr[k] : addr[0]) * UB);
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                float f[VEC];
+                unpack_unit<T, NW>(xr[k], f);          // re-read unit 0 on tail lanes is harmless for min / max
+#pragma unroll
+                for (int e = 0; e < VEC; e++) { mn = nan_min(mn, f[e]); mx = nan_max(mx, f[e]); }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                if (!ok[k]) continue;
+                const float v = Tr::to_f(xp[addr[k]]);
+                mn = nan_min(mn, v); mx = nan_max(mx, v);
+            }
+        }
+    }
+    // group reduction (min / max are order independent: deterministic by construction)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (G != 32) {
+        const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+        constexpr int NWARP = THREADS / 32;
+        if (lane == 0) { red[wi] = mn; red[32 + wi] = mx; }
+        __syncthreads();
+        if (wi == 0) {
+            mn = lane < NWARP ? red[lane] : __int_as_float(0x7f800000);
+            mx = lane < NWARP ? red[32 + lane] : __int_as_float(0xff800000);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+        }
+        __syncthreads();
+    }
+    if (sg.splits > 1) {
+        if (tg == 0) {
+            sg.partials[2 * tl.ltile] = (double)mn;
+            sg.partials[2 * tl.ltile + 1] = (double)mx;
+            __threadfence();
+            const unsigned prev = atomicAdd(&sg.counters[tl.c], 1u);
+            last_flag[grp] = (prev == (unsigned)sg.splits - 1u);
+        }
+        group_sync<G, THREADS>();
+        if (!last_flag[grp]) return;
+        __threadfence();
+        mn = __int_as_float(0x7f800000); mx = __int_as_float(0xff800000);
+        const double* p = sg.partials + 2 * (tl.c * sg.splits);
+        for (int i = tg; i < sg.splits; i += G) { mn = nan_min(mn, (float)__ldcg(p + 2 * i)); mx = nan_max(mx, (float)__ldcg(p + 2 * i + 1)); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (G != 32) {
+            const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+            constexpr int NWARP = THREADS / 32;
+            if (lane == 0) { red[wi] = mn; red[32 + wi] = mx; }
+            __syncthreads();
+            if (wi == 0) {
+                mn = lane < NWARP ? red[lane] : __int_as_float(0x7f800000);
+                mx = lane < NWARP ? red[32 + lane] : __int_as_float(0xff800000);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn = nan_min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = nan_max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+            }
+        }
+        if (tg == 0) sg.counters[tl.c] = 0u;
+    }
+    if (tg != 0) return;
+    // ---- observer update (torch/ao/quantization/observer.py: MinMaxObserver.forward, MovingAverageMinMaxObserver.forward)
+    float* min_state = reinterpret_cast<float*>(sg.gscale);
+    float* max_state = reinterpret_cast<float*>(sg.gshift);
+    float smin = min_state[tl.pidx], smax = max_state[tl.pidx];
+    const bool empty = (smin == __int_as_float(0x7f800000)) && (smax == __int_as_float(0xff800000));
+    if (sg.obs_flags & 2) {
+        if (empty) { smin = mn; smax = mx; }
+        else {
+            smin = __fadd_rn(smin, __fmul_rn(sg.obs_c, __fsub_rn(mn, smin)));
+            smax = __fadd_rn(smax, __fmul_rn(sg.obs_c, __fsub_rn(mx, smax)));
+        }
+    } else {
+        smin = nan_min(mn, smin); smax = nan_max(mx, smax);
+    }
+    min_state[tl.pidx] = smin; max_state[tl.pidx] = smax;
+    // ---- qparams (UniformQuantizationObserverBase._calculate_qparams) and LSQ parameters (observers.py:346-373)
+    float* scale_out = reinterpret_cast<float*>(sg.y);
+    float* shift_out = reinterpret_cast<float*>(sg.gx);
+    if (scale_out == nullptr) return;
+    const float min_neg = nan_min(smin, 0.0f);
+    float max_pos = nan_max(smax, 0.0f);
+    // torch divides a CUDA tensor by a Python scalar as a multiplication by the fp32 reciprocal
+    // (ATen BinaryDivTrueKernel.cu: inv_b = 1 / b; a * inv_b); tensor / tensor is a true division
+    const float range = __fsub_rn(sg.qmax, sg.qmin);            // float(quant_max - quant_min), exact for 8-bit ranges
+    float scale, zp;
+    if (sg.obs_flags & 1) {
+        max_pos = nan_max(-min_neg, max_pos);
+        scale = nan_max(__fmul_rn(max_pos, __fdiv_rn(1.0f, __fmul_rn(range, 0.5f))), sg.obs_eps);
+        zp = (float)sg.obs_zp_sym;
+    } else {
+        scale = nan_max(__fmul_rn(__fsub_rn(max_pos, min_neg), __fdiv_rn(1.0f, range)), sg.obs_eps);
+        zp = __fsub_rn(sg.qmin, rintf(__fdiv_rn(min_neg, scale)));
+        zp = fminf(fmaxf(zp, sg.qmin), sg.qmax);
+    }
+    scale_out[tl.pidx] = scale;
+    if (shift_out != nullptr) shift_out[tl.pidx] = __fmul_rn(-zp, scale);
 }
 
 }  // namespace lsqb200

@@ -45,6 +45,7 @@ inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int grou
     return get_bwd_kernel_bf16(mode, nw, bmode, group);
 }
 KernelFn get_stats_kernel(int xdtype, int nw, int group);
+KernelFn get_observe_kernel(int xdtype, int nw, int group);
 
 // Fixed workspace layout (see lsqb200_workspace_bytes): tickets first, partials after.
 constexpr long long kMaxCounters = 4096;     // channels that may be split across tiles

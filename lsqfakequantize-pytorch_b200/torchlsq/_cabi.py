@@ -30,6 +30,12 @@ class Segment(Structure):
                 ("q", QArgs)]
 
 
+class ObserverArgs(Structure):
+    """lsqb200_observer_args -- what torch's MinMax / MovingAverageMinMax observers need."""
+    _fields_ = [("quant_min", c_int64), ("quant_max", c_int64), ("averaging_constant", c_double), ("eps", c_double),
+                ("moving_average", c_int32), ("symmetric", c_int32), ("zero_point_sym", c_int32), ("reserved", c_int32)]
+
+
 class LaunchInfo(Structure):
     _fields_ = [("regime", c_int32), ("vec", c_int32), ("threads", c_int32), ("splits", c_int32),
                 ("grid", c_int64), ("units_per_split", c_int64)]
@@ -51,6 +57,8 @@ _PROTOTYPES = {
                                     c_void_p, c_size_t, c_void_p]),
     "lsqb200_weight_init_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
                                           c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
+    "lsqb200_observe": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                POINTER(ObserverArgs), c_void_p, c_size_t, c_void_p]),
     "lsqb200_plan_create": (c_int, [POINTER(Segment), c_int32, POINTER(c_void_p)]),
     "lsqb200_plan_forward": (c_int, [c_void_p, c_void_p]),
     "lsqb200_plan_backward": (c_int, [c_void_p, c_void_p]),

@@ -9,7 +9,9 @@ What is native here:
   * the fake-quant call itself (`torchlsq.functional.lsq` -> sm_100a kernels),
   * the mu +- 3 sigma weight initialisation: ONE fused pass (`lsqb200_weight_init_stats`) instead
     of `torch.mean` + `torch.std`,
-  * the learned initialisation (`init_mode=True` through the same kernels).
+  * the learned initialisation (`init_mode=True` through the same kernels),
+  * the observer initialisation (`init_mode='observer'`, the default): one fused pass per forward
+    (`lsqb200_observe`) instead of torch's `x.to(float32)` + `aminmax` + ~15 tiny kernels + host syncs.
 Everything else is Python control flow with the reference's semantics.  Two deliberate fixes:
 `with_args` works (the reference forgot `from functools import partial`), and the
 state-machine tests (`current_batch <= n_batches`, ...) read Python-side mirrors of the buffers,
@@ -110,6 +112,64 @@ def weight_init_scale(w: Tensor, ch_axis: int, per_channel: bool, quant_min: int
     return out
 
 
+_NATIVE_OBSERVERS = {
+    # observer class -> (per_channel, moving_average)
+    torch.quantization.MinMaxObserver: (False, False),
+    torch.quantization.MovingAverageMinMaxObserver: (False, True),
+    torch.quantization.PerChannelMinMaxObserver: (True, False),
+    torch.quantization.MovingAveragePerChannelMinMaxObserver: (True, True),
+}
+_SUPPORTED_OBS_QSCHEMES = (torch.per_tensor_affine, torch.per_tensor_symmetric, torch.per_channel_affine, torch.per_channel_symmetric)
+
+
+def observer_step(obs, x: Tensor, scale: Tensor, shift: Tensor) -> bool:
+    """One fused pass replacing `obs(x)`, `obs.calculate_qparams()` and `_set_weights(scale, zero_point)`
+    (observers.py:446-449) for torch's MinMax / MovingAverageMinMax observers and their PerChannel variants:
+    x is read ONCE in its own dtype (torch first materialises `x.to(float32)`, then runs `aminmax`, then ~15 tiny
+    kernels and two host syncs for the qparams); the running min / max buffers of `obs` and the LSQ `scale` / `shift`
+    parameters are updated in place with bit-identical fp32 arithmetic.  Returns False (and does nothing) when the
+    observer is of another kind - the caller then runs the torch observer as the reference does."""
+    from ...extension import _DT, _dense_layout, _stream_ptr, _workspace
+    kind = _NATIVE_OBSERVERS.get(type(obs))
+    if kind is None or not x.is_cuda or x.dtype not in _DT or x.numel() == 0:
+        return False
+    per_channel, moving = kind
+    if obs.qscheme not in _SUPPORTED_OBS_QSCHEMES or obs.min_val.dtype != torch.float32:
+        return False
+    if scale.dtype != torch.float32 or shift.dtype != torch.float32 or scale.device != x.device:
+        return False
+    nparam = x.shape[obs.ch_axis] if per_channel else 1
+    if scale.numel() != nparam or shift.numel() != nparam:
+        return False                                  # per-tensor observer on a per-channel quantizer or vice versa
+    if obs.min_val.device != x.device:
+        obs.to(x.device)                              # state follows the data (the torch path would sync on every copy_)
+    if obs.min_val.numel() != nparam or (per_channel and obs.min_val.dim() != 1):
+        obs.min_val.resize_(nparam).fill_(float("inf"))      # torch's "never observed" state
+        obs.max_val.resize_(nparam).fill_(float("-inf"))
+    cache = obs.__dict__.get("_lsqb200_args")
+    if cache is None:
+        sym = obs.qscheme in (torch.per_tensor_symmetric, torch.per_channel_symmetric)
+        zp_sym = 0
+        if obs.dtype in (torch.quint8, torch.uint8):
+            zp_sym = (obs.quant_min + obs.quant_max) // 2 if obs.has_customized_qrange else 128
+        cache = _cabi.ObserverArgs(int(obs.quant_min), int(obs.quant_max), float(getattr(obs, "averaging_constant", 1.0)),
+                                   float(obs.eps), int(moving), int(sym), int(zp_sym), 0)
+        obs.__dict__["_lsqb200_args"] = cache
+    lib = _cabi.load()
+    xd = x.detach()
+    if per_channel:
+        xd, outer, C, inner = _dense_layout(xd, obs.ch_axis)
+    else:
+        xd, outer, C, inner = _dense_layout(xd)
+    with torch.cuda.device(x.device):
+        sp = _stream_ptr(x.device)
+        ws = _workspace(x.device, sp)
+        rc = lib.lsqb200_observe(xd.data_ptr(), outer, C, inner, _DT[x.dtype], int(per_channel), obs.min_val.data_ptr(),
+                                 obs.max_val.data_ptr(), scale.data_ptr(), shift.data_ptr(), cache, ws.data_ptr(), ws.numel(), sp)
+    _cabi.check(rc, "lsqb200_observe")
+    return True
+
+
 class LSQFakeQuantizer(ObserverBase):
     """Fake-quantize module with learned step size (LSQ / LSQ+, arXiv:1902.08153, arXiv:2004.09576).
 
@@ -194,6 +254,7 @@ class LSQFakeQuantizer(ObserverBase):
         self.is_affine = IS_QSCHEME_AFFINE(self.qscheme)
         self.init_scale = init_scale
         self.init_shift = init_shift
+        self.native_observer = True          # set False to force torch's own observer kernels (debugging)
         self.quant_min, self.quant_max = self._verify_qmin_qmax(quant_min, quant_max, lowbit=avoid_torch_overflow)
         self.reset(learn_params=learn_params)
 
@@ -370,9 +431,11 @@ class LSQFakeQuantizer(ObserverBase):
             self._m_batch += 1
 
         if self._m_obs == 1:
-            self.activation_post_process(x.detach())
-            scale, zero_point = self.activation_post_process.calculate_qparams()
-            self._set_weights(scale=scale, zero_point=zero_point)
+            # fused native step for torch's MinMax-family observers; any other observer runs as in the reference
+            if not (self.native_observer and observer_step(self.activation_post_process, x, self.scale.data, self.shift.data)):
+                self.activation_post_process(x.detach())
+                scale, zero_point = self.activation_post_process.calculate_qparams()
+                self._set_weights(scale=scale, zero_point=zero_point)
 
         if self._m_fq == 1:
             backprop_init = backprop_init and full_lsq

@@ -397,3 +397,89 @@ def test_bit_exact_against_reference_cuda_op(tmp_path):
         report[name] = dict(gs_mine=float(gs.flatten()[0]), gs_ref=float(r_["gs"].float().flatten()[0]))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
     (ROOT / "gpurun_out" / "ref_cuda_parity.json").write_text(json.dumps(report, indent=1))
+
+
+# ------------------------------------------------------------------------------------------------
+# fused observer step (init_mode='observer') vs torch's own observers + the module's host logic
+# ------------------------------------------------------------------------------------------------
+def _torch_observer_path(obs, x, scale, shift):
+    """what observers.py:446-449 + :346-373 do: observer forward, calculate_qparams, _set_weights"""
+    obs(x.detach())
+    s, zp = obs.calculate_qparams()
+    with torch.no_grad():
+        scale.copy_(s.to(scale.device).to(scale.dtype).reshape(scale.shape))
+        shift.copy_((-zp.to(scale.device) * scale).to(shift.dtype).reshape(shift.shape))
+
+
+@pytest.mark.parametrize("cls,kw,per_channel", [
+    (torch.quantization.MovingAverageMinMaxObserver, dict(dtype=torch.quint8, qscheme=torch.per_tensor_affine, reduce_range=True), False),
+    (torch.quantization.MovingAverageMinMaxObserver, dict(dtype=torch.quint8, qscheme=torch.per_tensor_affine, averaging_constant=0.3), False),
+    (torch.quantization.MinMaxObserver, dict(dtype=torch.quint8, qscheme=torch.per_tensor_symmetric), False),
+    (torch.quantization.MinMaxObserver, dict(dtype=torch.qint8, qscheme=torch.per_tensor_symmetric, quant_min=-64, quant_max=63), False),
+    (torch.quantization.MovingAveragePerChannelMinMaxObserver, dict(dtype=torch.quint8, qscheme=torch.per_channel_affine, ch_axis=1), True),
+    (torch.quantization.PerChannelMinMaxObserver, dict(dtype=torch.qint8, qscheme=torch.per_channel_symmetric, ch_axis=0), True),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_observer_step_bit_exact_vs_torch_observers(cls, kw, per_channel, dtype):
+    import warnings
+    from torchlsq.quantized.modules.observers import observer_step
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = cls(**kw).to(U.DEV)
+        nat = cls(**kw).to(U.DEV)
+    ax = kw.get("ch_axis", None)
+    shape = (6, 24, 10, 10)
+    n = shape[ax] if per_channel else 1
+    s_ref, b_ref = torch.ones(n, device=U.DEV), torch.zeros(n, device=U.DEV)
+    s_nat, b_nat = torch.ones(n, device=U.DEV), torch.zeros(n, device=U.DEV)
+    gen = torch.Generator().manual_seed(3)
+    for step in range(5):
+        x = (torch.randn(*shape, generator=gen) * (1 + step) + 0.3 * step).to(dtype).to(U.DEV)
+        if step == 3:
+            x = x.abs()                       # all-positive batch: min_neg clamps at 0
+        _torch_observer_path(ref, x, s_ref, b_ref)
+        assert observer_step(nat, x, s_nat, b_nat)
+        assert torch.equal(nat.min_val.reshape(-1), ref.min_val.reshape(-1)), (step, nat.min_val, ref.min_val)
+        assert torch.equal(nat.max_val.reshape(-1), ref.max_val.reshape(-1)), step
+        assert torch.equal(s_nat, s_ref), (step, s_nat, s_ref)
+        assert torch.equal(b_nat, b_ref), (step, b_nat, b_ref)
+    # qparams exported by the torch observer object agree (its state was updated in place)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        s1, z1 = nat.calculate_qparams()
+        s2, z2 = ref.calculate_qparams()
+    assert torch.equal(s1, s2) and torch.equal(z1, z2)
+
+
+def test_observer_step_large_tensor_and_nan():
+    from torchlsq.quantized.modules.observers import observer_step
+    obs = torch.quantization.MinMaxObserver(dtype=torch.quint8, qscheme=torch.per_tensor_affine).to(U.DEV)
+    x = torch.empty(64 * 256 * 56 * 56, dtype=torch.bfloat16, device=U.DEV).normal_(0, 2, generator=torch.Generator(U.DEV).manual_seed(0))
+    s, b = torch.ones(1, device=U.DEV), torch.zeros(1, device=U.DEV)
+    assert observer_step(obs, x, s, b)
+    mn, mx = torch.aminmax(x.float())
+    assert obs.min_val.item() == mn.item() and obs.max_val.item() == mx.item()
+    assert s.item() == pytest.approx((mx.item() - mn.item()) / 255.0, rel=1e-6)
+    x[12345] = float("nan")                   # torch.aminmax propagates NaN; so does the fused step
+    assert observer_step(obs, x, s, b)
+    assert torch.isnan(obs.min_val).item() and torch.isnan(obs.max_val).item()
+    # unsupported observer kinds are left to torch
+    h = torch.quantization.HistogramObserver().to(U.DEV)
+    assert observer_step(h, x[:1000], s, b) is False
+
+
+def test_module_observer_mode_native_equals_torch_path():
+    from torchlsq import LSQFakeQuantizer
+    MA = torch.quantization.MovingAverageMinMaxObserver
+    torch.manual_seed(0)
+    a = LSQFakeQuantizer(MA, 'activation', init_mode='observer', init_batches=3).to(U.DEV)
+    b = LSQFakeQuantizer(MA, 'activation', init_mode='observer', init_batches=3).to(U.DEV)
+    b.native_observer = False
+    a.train(); b.train()
+    for i in range(7):
+        x = (torch.randn(8, 16, 12, 12, device=U.DEV) * (1 + 0.2 * i)).to(torch.bfloat16)
+        ya, yb = a(x), b(x)
+        assert torch.equal(ya, yb), i
+        if i >= 1:
+            assert torch.equal(a.scale, b.scale) and torch.equal(a.shift, b.shift), i
+    assert int(a.observer_enabled[0]) == 0 and int(b.observer_enabled[0]) == 0

@@ -159,6 +159,23 @@ def main():
         lib.lsqb200_bwd_channel(g4.data_ptr(), x4.data_ptr(), gx4.data_ptr(), sc.data_ptr(), bc.data_ptr(), gsc.data_ptr(), gbc.data_ptr(),
                                 256 * 196, 1024, 1, 1, 0, q, ws.data_ptr(), ws.numel(), sp)
     report("per_channel_fp16_channels_last_50176x1024_fwd_bwd", 5 * 2 * nn_, *timed(cl, 5, None), l2="large", launches=2)
+    # ---- observer-mode init step: fused native step vs torch's observer + host logic, 256x256x56x56 bf16
+    import warnings
+    from torchlsq.quantized.modules.observers import observer_step
+    xo = torch.empty(256 * 256 * 56 * 56, dtype=torch.bfloat16, device=DEV).normal_()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obs_n = torch.quantization.MovingAverageMinMaxObserver(reduce_range=True).to(DEV)
+        obs_t = torch.quantization.MovingAverageMinMaxObserver(reduce_range=True).to(DEV)
+    so, bo = torch.ones(1, device=DEV), torch.zeros(1, device=DEV)
+
+    def torch_path():
+        obs_t(xo)
+        sc, zp = obs_t.calculate_qparams()
+        so.copy_(sc); bo.copy_(-zp * so)
+    report("observer_step_native_bf16_411MB", 2 * xo.numel(), *timed(lambda: observer_step(obs_n, xo, so, bo), args.iters, None), l2="411 MB", launches=1)
+    report("observer_step_torch_path_bf16_411MB", 2 * xo.numel(), *timed(torch_path, max(5, args.iters // 2), None), l2="411 MB",
+           note="x.to(float32) + aminmax + qparams kernels + host syncs, as the reference module does")
     print(json.dumps(out, indent=1))
 
 
