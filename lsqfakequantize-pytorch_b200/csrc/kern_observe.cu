@@ -4,7 +4,7 @@ namespace lsqb200 {
 namespace {
 template <typename T, int NW>
 KernelFn pick_g(int group) {
-#define LSQ_O(G_) lsq_observe_kernel<T, NW, G_, kThreads, unroll_for(kUnrollStats, NW, G_), kLd, kMinBlocksStats>
+#define LSQ_O(G_) lsq_observe_kernel<T, NW, G_, kThreads, unroll_for(8, NW, 256), kLd, 4>   // read-only stream: 4 x 256-bit units in flight per thread
     return group == 32 ? LSQ_O(32) : LSQ_O(kThreads);
 #undef LSQ_O
 }
