@@ -124,6 +124,30 @@ LSQB200_API int lsqb200_observe(const void* x, int64_t outer, int64_t C, int64_t
                     float* min_val, float* max_val, float* scale_out, float* shift_out,
                     const lsqb200_observer_args* args, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- integer export, the step after QAT: real uint8 / int8 tensors and
+ *      torch-style qparams made on the device.  `codes` is uint8 (codes_signed == 0, quint8) or int8
+ *      (codes_signed == 1, qint8), same (outer, C, inner) box as x, 1 byte per element.
+ *      LSQB200_SEM_LSQ:   the integer the training forward forms (csrc/ops/kernels/lsq_kernel.h:12-13):
+ *                         rint(clamp(x/s + zp, quant_min, quant_max)); dequantize(codes) == lsq forward, bit for bit.
+ *      LSQB200_SEM_TORCH: LSQFakeQuantizer.calculate_qparams() (quantized/modules/observers.py:378-422:
+ *                         scale = max(scale, eps), zero_point = clamp(round(-shift/scale), type range)) followed by
+ *                         torch.quantize_per_tensor / quantize_per_channel on CUDA - what
+ *                         torch.quantization.convert does with this module.  Needs float32 scale / shift. ------- */
+#define LSQB200_SEM_LSQ 0
+#define LSQB200_SEM_TORCH 1      /* torch's CUDA quantizers: nearbyint(double(x) / double(scale)) + zero_point */
+#define LSQB200_SEM_TORCH_CPU 2  /* torch's CPU quantizers (fbgemm / quantize_val): nearbyint(x * (1.0f / scale)) + zero_point */
+LSQB200_API int lsqb200_quantize(const void* x, void* codes, const void* scale, const void* shift,
+                     int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype, int per_channel,
+                     const lsqb200_qargs* q, int codes_signed, int semantics, void* stream);
+/* y = (code - zp) * s with zp, s as defined by `semantics` */
+LSQB200_API int lsqb200_dequantize(const void* codes, void* y, const void* scale, const void* shift,
+                       int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype, int per_channel,
+                       const lsqb200_qargs* q, int codes_signed, int semantics, void* stream);
+/* calculate_qparams on the device: scale_out[i] = max(scale[i], eps) (float), zero_point_out[i] (int64, may be
+ * NULL) = clamp(round(-shift[i] / scale_out[i]), type_min, type_max).  No host round trip, no sync. */
+LSQB200_API int lsqb200_qparams(const void* scale, const void* shift, float* scale_out, int64_t* zero_point_out,
+                    int64_t n, int pdtype, int64_t type_min, int64_t type_max, void* stream);
+
 /* ---- multi-tensor plans: one launch for many fake-quant sites (the 54 ResNet-50 weights, or
  *      every site of a step).  Semantics per segment are exactly those of the calls above. --- */
 typedef struct lsqb200_segment {

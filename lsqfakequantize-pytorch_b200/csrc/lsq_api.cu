@@ -16,6 +16,7 @@
 #include "../../include/lsq_b200.h"
 #include "lsq_host.h"
 #include "lsq_column.cuh"
+#include "lsq_export.cuh"
 
 using namespace lsqb200;
 
@@ -242,6 +243,35 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
     const Seg seg = make_seg(a, g, partials, counters, 0);
     KernelFn k = get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, st);
+}
+
+int export_common(int dir, const void* fl, void* codes, const void* scale, const void* shift, int64_t outer, int64_t C,
+                  int64_t inner, int xdt, int pdt, int per_channel, const lsqb200_qargs* q, int codes_signed, int sem,
+                  void* stream) {
+    if (int r = check_q(q)) return r;
+    if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
+    if (xdt < 0 || xdt > 2 || pdt < 0 || pdt > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    if (sem != SEM_LSQ && sem != SEM_TORCH && sem != SEM_TORCH_CPU) return fail(LSQB200_ERR_ARG, "unknown code semantics");
+    const int mode = pick_mode(xdt, pdt);
+    if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
+    if (sem != SEM_LSQ && pdt != DT_F32) return fail(LSQB200_ERR_DTYPE, "torch semantics need float32 scale / shift");
+    if (q->type_min < -128 || q->type_max > 255 || q->quant_min < -128 || q->quant_max > 255 ||
+        (codes_signed ? (q->quant_max > 127 || (sem != SEM_LSQ && q->type_max > 127))
+                      : (q->quant_min < 0 || (sem != SEM_LSQ && q->type_min < 0))))
+        return fail(LSQB200_ERR_ARG, "range does not fit the 8-bit code type");
+    if (outer * C * inner == 0) return 0;
+    if (!fl || !codes || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    // a unit of the floating tensor (<= 32 B) covers unit/elem_size code bytes: both sides must be aligned to their unit
+    const int es = elem_size(xdt);
+    int al = common_alignment({fl});
+    const int alc = common_alignment({codes}) * es;
+    if (alc < al) al = alc;
+    const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, al, tuning());
+    SegArgs a = seg_args(fl, codes, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
+    Seg seg = make_seg(a, g, nullptr, nullptr, 0);
+    seg.code_signed = codes_signed ? 1 : 0;
+    KernelFn k = get_export_kernel(xdt, mode, g.nw, sem, dir, g.group);
+    return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
 }  // namespace
@@ -499,6 +529,35 @@ int lsqb200_observe(const void* x, int64_t outer, int64_t C, int64_t inner, int 
     seg.obs_zp_sym = oa->zero_point_sym;
     KernelFn k = get_observe_kernel(xdtype, g.nw, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
+}
+
+int lsqb200_quantize(const void* x, void* codes, const void* scale, const void* shift, int64_t outer, int64_t C, int64_t inner,
+                     int xdtype, int pdtype, int per_channel, const lsqb200_qargs* q, int codes_signed, int semantics,
+                     void* stream) {
+    if (!per_channel) { inner *= outer * C; outer = 1; C = 1; }
+    return export_common(DIR_QUANT, x, codes, scale, shift, outer, C, inner, xdtype, pdtype, per_channel ? 1 : 0, q,
+                         codes_signed, semantics, stream);
+}
+
+int lsqb200_dequantize(const void* codes, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
+                       int64_t inner, int xdtype, int pdtype, int per_channel, const lsqb200_qargs* q, int codes_signed,
+                       int semantics, void* stream) {
+    if (!per_channel) { inner *= outer * C; outer = 1; C = 1; }
+    return export_common(DIR_DEQUANT, y, const_cast<void*>(codes), scale, shift, outer, C, inner, xdtype, pdtype,
+                         per_channel ? 1 : 0, q, codes_signed, semantics, stream);
+}
+
+int lsqb200_qparams(const void* scale, const void* shift, float* scale_out, int64_t* zero_point_out, int64_t n, int pdtype,
+                    int64_t type_min, int64_t type_max, void* stream) {
+    if (n < 0) return fail(LSQB200_ERR_ARG, "negative size");
+    if (pdtype < 0 || pdtype > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    if (type_min > type_max) return fail(LSQB200_ERR_ARG, "type_min must not exceed type_max");
+    if (n == 0) return 0;
+    if (!scale || !shift || !scale_out) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    const int e = launch_qparams(scale, shift, scale_out, reinterpret_cast<long long*>(zero_point_out), n, pdtype,
+                                 (float)type_min, (float)type_max, tuning().pdl != 0, (cudaStream_t)stream);
+    if (e != 0) return cuda_fail((cudaError_t)e, "kernel launch");
+    return 0;
 }
 
 int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan** out) {

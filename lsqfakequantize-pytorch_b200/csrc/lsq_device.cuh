@@ -75,6 +75,9 @@ struct Seg {
     float obs_c, obs_eps;  // averaging constant, eps
     int obs_flags;         // bit 0: symmetric qscheme, bit 1: moving average (else running extrema)
     int obs_zp_sym;        // zero point of the symmetric scheme (0, 128 or (qmin+qmax)//2)
+    // integer export (lsq_export.cuh): y holds uint8 / int8 codes
+    int code_signed;       // 1: int8 codes (qint8), 0: uint8 (quint8)
+    int reserved0;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -46,6 +46,10 @@ inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int grou
 }
 KernelFn get_stats_kernel(int xdtype, int nw, int group);
 KernelFn get_observe_kernel(int xdtype, int nw, int group);
+// kern_export.cu: dir 0 = quantize (x -> uint8 / int8 codes), 1 = dequantize; sem 0 = LSQ forward's integer, 1 = torch.quantize_per_*
+KernelFn get_export_kernel(int xdtype, int mode, int nw, int sem, int dir, int group);
+int launch_qparams(const void* scale, const void* shift, float* scale_out, long long* zp_out, long long n, int pdt,
+                   float tmin, float tmax, bool pdl, cudaStream_t st);
 
 // Fixed workspace layout (see lsqb200_workspace_bytes): tickets first, partials after.
 constexpr long long kMaxCounters = 4096;     // channels that may be split across tiles

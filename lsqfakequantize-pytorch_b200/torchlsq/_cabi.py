@@ -12,6 +12,7 @@ from pathlib import Path
 
 LIB_NAME = "libtorchlsq_b200.so"
 F32, F16, BF16 = 0, 1, 2
+SEM_LSQ, SEM_TORCH, SEM_TORCH_CPU = 0, 1, 2
 
 
 class QArgs(Structure):
@@ -59,6 +60,11 @@ _PROTOTYPES = {
                                           c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "lsqb200_observe": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                 POINTER(ObserverArgs), c_void_p, c_size_t, c_void_p]),
+    "lsqb200_quantize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
+                                 POINTER(QArgs), c_int, c_int, c_void_p]),
+    "lsqb200_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
+                                   POINTER(QArgs), c_int, c_int, c_void_p]),
+    "lsqb200_qparams": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p]),
     "lsqb200_plan_create": (c_int, [POINTER(Segment), c_int32, POINTER(c_void_p)]),
     "lsqb200_plan_forward": (c_int, [c_void_p, c_void_p]),
     "lsqb200_plan_backward": (c_int, [c_void_p, c_void_p]),

@@ -46,6 +46,11 @@ def lib():
         _lib.lsq_oracle_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(Cfg)]
         _lib.lsq_oracle_weight_init.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64]
+        _lib.lsq_oracle_qparams.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64]
+        _lib.lsq_oracle_quantize.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                             c_int, POINTER(Cfg), c_int]
+        _lib.lsq_oracle_dequantize.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                               c_int, POINTER(Cfg), c_int]
         _lib.lsq_oracle_h2f.restype = c_float
         _lib.lsq_oracle_h2f.argtypes = [ctypes.c_uint16]
         _lib.lsq_oracle_f2h.restype = ctypes.c_uint16
@@ -129,6 +134,42 @@ def weight_init(w, quant_min, quant_max, outer=1, C=1, inner=None, dt=None):
     out = np.empty(C, np.float32)
     lib().lsq_oracle_weight_init(_p(wr), dt, _p(out), outer, C, inner, int(quant_min), int(quant_max))
     return out
+
+
+SEM_LSQ, SEM_TORCH_CUDA, SEM_TORCH_CPU = 0, 1, 2
+
+
+def qparams(scale, shift, type_min, type_max):
+    """LSQFakeQuantizer.calculate_qparams(): (max(scale, eps) float32[n], zero_point int64[n])."""
+    s, b = _params(scale, shift)
+    so, zo = np.empty_like(s), np.empty(s.size, np.int64)
+    lib().lsq_oracle_qparams(_p(s), _p(b), _p(so), _p(zo), s.size, int(type_min), int(type_max))
+    return so, zo
+
+
+def quantize(x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None, sem=SEM_LSQ):
+    """int32 codes, one per element of x viewed as contiguous (outer, C, inner)."""
+    dt = _dt_of(x, dt)
+    xr = _raw(x)
+    inner = xr.size // (outer * C) if inner is None else inner
+    assert outer * C * inner == xr.size
+    s, b = _params(scale, shift)
+    codes = np.empty(xr.size, np.int32)
+    lib().lsq_oracle_quantize(_p(xr), dt, _p(codes), _p(s), _p(b), outer, C, inner, int(per_channel), ctypes.byref(c), int(sem))
+    return codes
+
+
+def dequantize(codes, like, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None, sem=SEM_LSQ):
+    """(code - zp) * s stored in `like`'s dtype / bit pattern."""
+    dt = _dt_of(like, dt)
+    lr = _raw(like)
+    codes = np.ascontiguousarray(codes, dtype=np.int32).reshape(-1)
+    inner = codes.size // (outer * C) if inner is None else inner
+    assert outer * C * inner == codes.size == lr.size
+    s, b = _params(scale, shift)
+    y = np.empty_like(lr)
+    lib().lsq_oracle_dequantize(_p(codes), _p(y), dt, _p(s), _p(b), outer, C, inner, int(per_channel), ctypes.byref(c), int(sem))
+    return y.view(like.dtype) if like.dtype == np.float16 else y
 
 
 # ---- torch <-> bit-pattern helpers (tests only) ---------------------------------------------
