@@ -345,10 +345,12 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, double* sm /* [
 // Programmatic dependent launch (sm_90+): let the NEXT kernel of the stream start launching while
 // this grid drains, and - when this grid itself was launched as a dependent - wait for the
 // previous grid to complete before touching any global memory.  No-ops for ordinary launches.
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
+// The wait is placed as LATE as possible: descriptor staging (kernel parameters / plan tables, which no
+// kernel ever writes), tile geometry and walker set-up run while the predecessor is still draining;
+// only the first access to tensor or parameter memory has to sit behind pdl_wait().
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
 
 // A group may walk several CONSECUTIVE tiles (rows of the same weight tensor, as a rule), so
 // the descriptor look-up and staging are paid once per few rows, not once per row.
@@ -483,7 +485,7 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     __shared__ Seg smem_seg[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
     constexpr int ROWS = tiles_per_group(G);
-    pdl_prologue();
+    pdl_trigger();
     int staged = -2;
     for (int row_i = 0; row_i < ROWS; row_i++) {
     const long long gtile = ((long long)blockIdx.x * GROUPS + grp) * ROWS + row_i;
@@ -493,6 +495,9 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
     T* __restrict__ yp = reinterpret_cast<T*>(sg.y);
+    Walker w;
+    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, tl.pidx);
 
@@ -502,8 +507,6 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
             yp[e] = INIT ? xp[e] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xp[e]), lch.get(sg)));
         }
     }
-    Walker w;
-    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
     while (w.more()) {
         long long addr[UNROLL];
         bool ok[UNROLL];
@@ -584,7 +587,7 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     __shared__ int last_flag[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
     constexpr int ROWS = tiles_per_group(G);
-    pdl_prologue();
+    pdl_trigger();
     int staged = -2;
     for (int row_i = 0; row_i < ROWS; row_i++) {
     const long long gtile = ((long long)blockIdx.x * GROUPS + grp) * ROWS + row_i;
@@ -596,6 +599,9 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const T* __restrict__ gp = reinterpret_cast<const T*>(sg.g);
     T* __restrict__ gxp = reinterpret_cast<T*>(sg.gx);
     const bool write_gx = gxp != nullptr;
+    Walker w;
+    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, tl.pidx);
 
@@ -607,8 +613,6 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
             if (write_gx) gxp[e] = bmode_passthrough(BMODE) ? gp[e] : Tr::from_f(dx);
         }
     }
-    Walker w;
-    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
     while (w.more()) {
         long long addr[UNROLL];
         bool ok[UNROLL];
@@ -687,7 +691,7 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
     __shared__ int last_flag[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
     constexpr int ROWS = tiles_per_group(G);
-    pdl_prologue();
+    pdl_trigger();
     int staged = -2;
     for (int row_i = 0; row_i < ROWS; row_i++) {
     const long long gtile = ((long long)blockIdx.x * GROUPS + grp) * ROWS + row_i;
@@ -696,6 +700,7 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
     const Seg& sg = smem_seg[grp];
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    pdl_wait();
     const float pivot = Tr::to_f(xp[tl.c * sg.inner]);      // element (0, c, 0): shift that keeps the sums small
 
     // per unit: d = w - pivot, sum d and sum d^2 over the unit's <= 16 elements in fp32 (FADD / FFMA),

@@ -112,7 +112,7 @@ lsq_export_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ ta
     constexpr int GROUPS = THREADS / G;
     __shared__ Seg smem_seg[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
-    pdl_prologue();
+    pdl_trigger();
     int staged = -2;
     const long long gtile = (long long)blockIdx.x * GROUPS + grp;
     if (gtile >= total_tiles) return;
@@ -123,6 +123,9 @@ lsq_export_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ ta
     uint8_t* __restrict__ cp = reinterpret_cast<uint8_t*>(sg.y);
     const bool is_signed = sg.code_signed != 0;
     const bool perch = sg.per_channel != 0;
+    Walker w;
+    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    pdl_wait();
     const Chan ch = make_chan_export<MODE, SEM>(load_param(sg.scale, tl.pidx, sg.pdt), load_param(sg.shift, tl.pidx, sg.pdt), sg);
 
     if constexpr (VEC > 1) {
@@ -132,8 +135,6 @@ lsq_export_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ ta
             else fp[e] = Tr::from_f(dequant_code(is_signed ? (int)(int8_t)cp[e] : (int)cp[e], ch));
         }
     }
-    Walker w;
-    w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
     while (w.more()) {
         long long addr[UNROLL];
         bool ok[UNROLL];

@@ -66,11 +66,14 @@ struct Tuning {
     // end of the launch (SMs do not progress at the same speed; a single wave of big equal
     // slices costs ~10 %); the backward pays one block reduction + ticket per tile, so its
     // tiles are larger.  Sizes are bytes of ONE operand.
-    int fwd_tile_kb = 32;
-    int bwd_tile_kb = 256;
+    int fwd_tile_kb = 64;
+    int bwd_tile_kb = 512;
     int stats_tile_kb = 128;
-    int fwd_min_tiles_per_sm = 16;   // small tensors: shrink tiles until the machine is full
-    int bwd_min_tiles_per_sm = 8;
+    // small tensors: shrink tiles until the machine is full - ONE wave of resident CTAs (6 / 4 per SM), not more:
+    // in-stream sweep over the ResNet-50 site sizes (tools/site_sweep.py, profiles/r1_site_sweep.md): a second,
+    // partly filled wave costs 2-3.5 us per backward launch on 6-50 M-element sites
+    int fwd_min_tiles_per_sm = 6;
+    int bwd_min_tiles_per_sm = 4;
     int warp_units = 1024;      // channels with <= this many units are owned by warp groups (all ResNet-50 weight rows)
     int min_iters = 1;          // never split below min_iters full group iterations
     int interleave = 1;         // 1: interleave the splits of a channel (grid-stride style), 0: contiguous slices

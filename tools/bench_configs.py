@@ -176,6 +176,21 @@ def main():
     report("observer_step_native_bf16_411MB", 2 * xo.numel(), *timed(lambda: observer_step(obs_n, xo, so, bo), args.iters, None), l2="411 MB", launches=1)
     report("observer_step_torch_path_bf16_411MB", 2 * xo.numel(), *timed(torch_path, max(5, args.iters // 2), None), l2="411 MB",
            note="x.to(float32) + aminmax + qparams kernels + host syncs, as the reference module does")
+    # ---- integer export: bf16 activation -> uint8 codes (3 B / element), codes -> bf16, vs torch's own path
+    from torchlsq import export as EX
+    s1, b1 = torch.tensor([0.03], device=DEV), torch.tensor([-1.7], device=DEV)
+    xe = xo.view(256, 256, 56, 56)
+    for sem in ("lsq", "torch"):
+        report(f"export_quantize_{sem}_bf16_to_u8_411MB", 3 * xe.numel(), *timed(lambda: EX.quantize(xe, s1, b1, 0, 127, 0, 255, semantics=sem), args.iters, None),
+               l2="411 MB in", launches=1)
+    ce = EX.quantize(xe, s1, b1, 0, 127, 0, 255)
+    report("export_dequantize_lsq_u8_to_bf16_205MB", 3 * xe.numel(), *timed(lambda: EX.dequantize(ce, s1, b1, 0, 127, 0, 255, dtype=torch.bfloat16), args.iters, None),
+           l2="205 MB in", launches=1)
+    xf = xe[:64].float()
+    report("export_torch_quantize_per_tensor_f32_205MB", 5 * xf.numel(), *timed(lambda: torch.quantize_per_tensor(xf, 0.03, 57, torch.quint8), max(5, args.iters // 2), None),
+           l2="205 MB in", note="torch's CUDA quantizer (fp32 input only), for comparison")
+    report("export_quantize_torch_f32_to_u8_205MB", 5 * xf.numel(), *timed(lambda: EX.quantize(xf, s1, b1, 0, 127, 0, 255, semantics='torch'), args.iters, None),
+           l2="205 MB in", launches=1)
     print(json.dumps(out, indent=1))
 
 
