@@ -52,6 +52,7 @@ int pick_mode(int xdt, int pdt) {
     if (xdt == DT_F16 && pdt == DT_F32) return M_FP32;
     if (xdt == DT_F16 && pdt == DT_F16) return M_HALF_EXACT;   // reference-exact c10::Half semantics
     if (xdt == DT_BF16 && (pdt == DT_F32 || pdt == DT_BF16)) return M_FP32;
+    if (xdt == DT_F64 && pdt == DT_F64) return M_F64;           // reference rule: scale.dtype == x.dtype (lsq_cuda.cu:34-35)
     return -1;
 }
 
@@ -99,7 +100,7 @@ int launch(KernelFn k, const Seg& seg, const Seg* table, const int* tile_seg, in
     return 0;
 }
 
-size_t param_size(int pdt) { return pdt == DT_F32 ? 4 : 2; }
+size_t param_size(int pdt) { return pdt == DT_F64 ? 8 : (pdt == DT_F32 ? 4 : 2); }
 
 // ---- column-layout path (short channel rows: channels-last, 7x7 / 14x14 maps) ------------------
 struct ColGeom { bool ok; int tx, ty; long long units_per_row, rows_per_split, col_blocks, row_splits; };
@@ -180,12 +181,13 @@ int forward_common(const void* x, void* y, const void* scale, const void* shift,
                    int64_t inner, int xdt, int pdt, int per_channel, const lsqb200_qargs* q, void* stream) {
     if (int r = check_q(q)) return r;
     if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
-    if (xdt < 0 || xdt > 2 || pdt < 0 || pdt > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    if (xdt < 0 || xdt > 3 || pdt < 0 || pdt > 3) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
     const int mode = pick_mode(xdt, pdt);
     if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
     if (outer * C * inner == 0) return 0;
     if (!x || !y || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
-    if (per_channel) {
+    if (xdt == DT_F64 && common_alignment({x, y, scale, shift}) < 8) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
+    if (per_channel && xdt != DT_F64) {
         ColKernelFn ck = get_col_fwd_kernel(xdt, mode, q->init_mode != 0, tuning().col_variant);
         const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, y}), tuning(), occupancy_of((const void*)ck, kColThreads));
         if (cg.ok) {
@@ -205,7 +207,7 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
                     const lsqb200_qargs* q, void* workspace, size_t wbytes, void* stream) {
     if (int r = check_q(q)) return r;
     if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
-    if (xdt < 0 || xdt > 2 || pdt < 0 || pdt > 2) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
+    if (xdt < 0 || xdt > 3 || pdt < 0 || pdt > 3) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
     const int mode = pick_mode(xdt, pdt);
     if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
     if (!gscale || !gshift) return fail(LSQB200_ERR_ARG, "NULL grad_scale / grad_shift pointer");
@@ -220,7 +222,9 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
         return 0;
     }
     if (!grad || !x || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
-    if (per_channel) {
+    if (xdt == DT_F64 && common_alignment({x, grad, gx, scale, shift, gscale, gshift}) < 8)
+        return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
+    if (per_channel && xdt != DT_F64) {
         ColKernelFn ck = get_col_bwd_kernel(xdt, mode, bmode_of(q), tuning().col_variant);
         const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads));
         if (cg.ok) {
@@ -317,7 +321,11 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         KernelFn k = nullptr;
         if (kind == K_FWD) { variant = s.q.init_mode != 0; k = get_fwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
         else if (kind == K_BWD) { variant = bmode_of(&s.q); k = get_bwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
-        else { k = get_stats_kernel(s.xdtype, g.nw, g.group); }
+        else {
+            if (s.xdtype == DT_F64) continue;   // no float64 statistics (the module cannot hold float64 weights): slot left untouched
+            k = get_stats_kernel(s.xdtype, g.nw, g.group);
+        }
+        if (!k) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
         const ClassKey key{s.xdtype, kind == K_STATS ? 0 : mode, g.nw, variant, g.group};
         auto it = index.find(key);
         if (it == index.end()) {
@@ -567,7 +575,7 @@ int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan*
     cudaGetDevice(&p->device);
     long long off = 0;
     for (const auto& s : p->segs) {
-        if (s.outer < 0 || s.C < 0 || s.inner < 0 || s.xdtype < 0 || s.xdtype > 2 || s.pdtype < 0 || s.pdtype > 2) {
+        if (s.outer < 0 || s.C < 0 || s.inner < 0 || s.xdtype < 0 || s.xdtype > 3 || s.pdtype < 0 || s.pdtype > 3) {
             delete p;
             return fail(LSQB200_ERR_PLAN, "bad segment (negative size or unknown dtype)");
         }

@@ -27,10 +27,11 @@
 
 namespace lsqb200 {
 
-enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_F64 = 3 };   // DT_F64: lsq_f64.cuh
 // MODE: how the affine value v = x/s + zp is formed
 enum : int { M_FP32 = 0,        // fp32 internal math (fp32 tensors; fp16/bf16 tensors up-cast)
-             M_HALF_EXACT = 1 };// fp16 x with fp16 params: round to half after every operator (c10::Half)
+             M_HALF_EXACT = 1,  // fp16 x with fp16 params: round to half after every operator (c10::Half)
+             M_F64 = 2 };       // float64 x with float64 params (lsq_f64.cuh)
 enum : int { B_NORMAL = 0, B_INIT = 1, B_EVAL = 2, B_EVAL_INIT = 3 };
 __host__ __device__ constexpr bool bmode_passthrough(int b) { return b == B_INIT || b == B_EVAL_INIT; }
 __host__ __device__ constexpr bool bmode_reduces(int b) { return b == B_NORMAL || b == B_INIT; }

@@ -39,11 +39,15 @@ KernelFn get_bwd_kernel_f16_mixed(int mode, int nw, int bmode, int group);
 KernelFn get_bwd_kernel_f16_exact(int mode, int nw, int bmode, int group);
 KernelFn get_bwd_kernel_bf16(int mode, int nw, int bmode, int group);
 inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int group) {
+    if (xdtype == DT_F64) return get_bwd_kernel_f64(nw, bmode, group);
     if (xdtype == DT_F32) return get_bwd_kernel_f32(mode, nw, bmode, group);
     if (xdtype == DT_F16) return mode == M_HALF_EXACT ? get_bwd_kernel_f16_exact(mode, nw, bmode, group)
                                                       : get_bwd_kernel_f16_mixed(mode, nw, bmode, group);
     return get_bwd_kernel_bf16(mode, nw, bmode, group);
 }
+// kern_f64.cu: float64 tensors (nullptr for nw == 0: doubles are 8-byte aligned or the call is rejected)
+KernelFn get_fwd_kernel_f64(int nw, bool init, int group);
+KernelFn get_bwd_kernel_f64(int nw, int bmode, int group);
 KernelFn get_stats_kernel(int xdtype, int nw, int group);
 KernelFn get_observe_kernel(int xdtype, int nw, int group);
 // kern_export.cu: dir 0 = quantize (x -> uint8 / int8 codes), 1 = dequantize; sem 0 = LSQ forward's integer, 1 = torch.quantize_per_*
@@ -94,7 +98,7 @@ struct Geometry {
     long long vpr, row_stride, chan_units, units_per_split, tiles, grid;
 };
 
-inline int elem_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+inline int elem_size(int dt) { return dt == DT_F64 ? 8 : (dt == DT_F32 ? 4 : 2); }
 
 inline Geometry plan_geometry(long long outer, long long C, long long inner, int xdtype, int kind,
                               int align_bytes, const Tuning& tn, int threads = kThreads, int unroll_override = 0) {

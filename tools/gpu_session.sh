@@ -13,7 +13,7 @@ if [ -f ab/lib_prev.so ]; then
   done
 fi
 python tools/bench_configs.py > $out/${tag}_configs.json 2>$out/${tag}_configs.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $out/${tag}_launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:lsq_ -c 1500 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-plan-mode > $out/${tag}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name regex:lsq_bwd_kernel --launch-skip 69 --launch-count 2 \
     -f -o $out/${tag}_prof_bwd python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-plan-mode > $out/${tag}_prof_bwd.log 2>&1

@@ -89,8 +89,11 @@ def report(rep, out_md, tags):
 
 
 def launches(csv_path, out_md):
+    """Per-kernel totals of a gpu__time_duration launch list.  Shares are taken over the PRODUCT kernels
+    (namespace lsqb200) only; whatever else the process launched (torch RNG / fill kernels that build the
+    synthetic inputs before the timed region) is listed separately."""
     lines = [ln for ln in open(csv_path) if not ln.startswith("==")]
-    agg = OrderedDict()
+    agg, other = OrderedDict(), OrderedDict()
     total = 0.0
     for r in csv.DictReader(lines):
         if r.get("Metric Name") != "gpu__time_duration.sum":
@@ -98,16 +101,24 @@ def launches(csv_path, out_md):
         name = r["Kernel Name"]
         short = name.split("(")[0][:110]
         t = float(r["Metric Value"].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r["Metric Unit"], 1e-3)
-        a = agg.setdefault(short, [0, 0.0])
+        mine = "lsqb200::" in name or "lsq_" in name.split("(")[0]
+        a = (agg if mine else other).setdefault(short, [0, 0.0])
         a[0] += 1
         a[1] += t
-        total += t
+        if mine:
+            total += t
     out = [f"# kernel launch list: `{Path(csv_path).name}`", "",
            "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py`; per-launch times are cold-cache and "
            "serialised, so only each kernel's SHARE of the step is meaningful.", "",
-           "| kernel | launches | total us | share |", "|---|---|---|---|"]
+           "## product kernels (the timed step)", "",
+           "| kernel | launches | total us | share of step |", "|---|---|---|---|"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f"| `{k}` | {n} | {t:.1f} | {100 * t / total:.1f} % |")
+    if other:
+        out += ["", "## other kernels in the capture (input generation and checks outside the timed region)", "",
+                "| kernel | launches | total us |", "|---|---|---|"]
+        for k, (n, t) in sorted(other.items(), key=lambda kv: -kv[1][1]):
+            out.append(f"| `{k}` | {n} | {t:.1f} |")
     Path(out_md).write_text("\n".join(out) + "\n")
     print("wrote", out_md)
 
