@@ -42,6 +42,12 @@ extern "C" {
 #define LSQB200_F32 0
 #define LSQB200_F16 1
 #define LSQB200_BF16 2
+/* float64 tensors with float64 scale / shift (the reference dispatches double too:
+ * AT_DISPATCH_FLOATING_TYPES_AND_HALF, csrc/ops/cuda/lsq_cuda.cu:45,113,186,266); accepted by the
+ * fwd / bwd calls and by plans, not by the statistics / observer / export calls.  The arithmetic
+ * is the reference CUDA build's: clamps go through ::fminf / ::fmaxf (csrc/ops/global_scope.h:51-52),
+ * i.e. through float -- see csrc/lsq_f64.cuh. */
+#define LSQB200_F64 3
 
 #define LSQB200_OK 0
 #define LSQB200_ERR_ARG (-1)        /* null pointer, negative size, bad flag */

@@ -3,7 +3,7 @@
 #include "lsq_f64.cuh"
 namespace lsqb200 {
 namespace {
-constexpr int kMinBlocksF64 = 3;
+constexpr int kMinBlocksF64 = 3, kMinBlocksF64Bwd = 2;   // register caps 85 / 128: no spills
 template <int NW, int G_>
 KernelFn pick_f(bool init) {
 #define LSQ_F(INIT_) lsq_fwd_f64_kernel<NW, INIT_, G_, kThreads, unroll_for(kUnrollFwd, NW, G_), kLd, kSt, kMinBlocksF64>
@@ -12,7 +12,7 @@ KernelFn pick_f(bool init) {
 }
 template <int NW, int G_>
 KernelFn pick_b(int bmode) {
-#define LSQ_B(B_) lsq_bwd_f64_kernel<NW, B_, G_, kThreads, unroll_for(kUnrollBwd, NW, G_), kLd, kSt, kMinBlocksF64>
+#define LSQ_B(B_) lsq_bwd_f64_kernel<NW, B_, G_, kThreads, unroll_for(kUnrollBwd, NW, G_), kLd, kSt, kMinBlocksF64Bwd>
     switch (bmode) {
         case B_NORMAL: return LSQ_B(B_NORMAL);
         case B_INIT: return LSQ_B(B_INIT);

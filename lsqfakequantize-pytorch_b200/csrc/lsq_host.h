@@ -34,6 +34,9 @@ constexpr int kSt = ST_DEFAULT;
 using KernelFn = void (*)(const Seg, const Seg*, const int*, int, long long);
 // defined in kern_fwd.cu / kern_bwd_*.cu / kern_stats.cu (one translation unit per family so they build in parallel)
 KernelFn get_fwd_kernel(int xdtype, int mode, int nw, bool init, int group);
+// kern_f64.cu: float64 tensors (nullptr for nw == 0: doubles are 8-byte aligned or the call is rejected)
+KernelFn get_fwd_kernel_f64(int nw, bool init, int group);
+KernelFn get_bwd_kernel_f64(int nw, int bmode, int group);
 KernelFn get_bwd_kernel_f32(int mode, int nw, int bmode, int group);
 KernelFn get_bwd_kernel_f16_mixed(int mode, int nw, int bmode, int group);
 KernelFn get_bwd_kernel_f16_exact(int mode, int nw, int bmode, int group);
@@ -45,9 +48,6 @@ inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int grou
                                                       : get_bwd_kernel_f16_mixed(mode, nw, bmode, group);
     return get_bwd_kernel_bf16(mode, nw, bmode, group);
 }
-// kern_f64.cu: float64 tensors (nullptr for nw == 0: doubles are 8-byte aligned or the call is rejected)
-KernelFn get_fwd_kernel_f64(int nw, bool init, int group);
-KernelFn get_bwd_kernel_f64(int nw, int bmode, int group);
 KernelFn get_stats_kernel(int xdtype, int nw, int group);
 KernelFn get_observe_kernel(int xdtype, int nw, int group);
 // kern_export.cu: dir 0 = quantize (x -> uint8 / int8 codes), 1 = dequantize; sem 0 = LSQ forward's integer, 1 = torch.quantize_per_*

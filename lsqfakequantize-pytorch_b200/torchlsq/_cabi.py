@@ -11,7 +11,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_in
 from pathlib import Path
 
 LIB_NAME = "libtorchlsq_b200.so"
-F32, F16, BF16 = 0, 1, 2
+F32, F16, BF16, F64 = 0, 1, 2, 3
 SEM_LSQ, SEM_TORCH, SEM_TORCH_CPU = 0, 1, 2
 
 

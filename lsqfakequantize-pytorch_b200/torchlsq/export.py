@@ -58,6 +58,8 @@ def quantize(x: Tensor, scale: Tensor, shift: Tensor, quant_min: int = 0, quant_
     type_min = quant_min if type_min is None else type_min
     type_max = quant_max if type_max is None else type_max
     _check_common(x, scale, shift)
+    if x.dtype not in _DT:
+        raise RuntimeError(f"integer export takes float32, float16 or bfloat16 tensors, got {x.dtype}")
     scale, shift = _prep(scale, shift, is_perchannel, x, axis)
     cdt = _code_dtype(code_dtype, type_min if semantics != 'lsq' else quant_min)
     xd, outer, C, inner = _dense_layout(x.detach(), axis if is_perchannel else None)
@@ -85,6 +87,8 @@ def dequantize(codes: Tensor, scale: Tensor, shift: Tensor, quant_min: int = 0, 
     cd, outer, C, inner = _dense_layout(codes, axis if is_perchannel else None)
     y = torch.empty_like(cd, dtype=dtype)
     _check_common(y, scale, shift, who_x='output')
+    if dtype not in _DT:
+        raise RuntimeError(f"integer export produces float32, float16 or bfloat16 tensors, got {dtype}")
     scale, shift = _prep(scale, shift, is_perchannel, codes, axis)
     q = _cabi.qargs(quant_min, quant_max, type_min, type_max, False, 1.0, False, False, False)
     with torch.cuda.device(codes.device):

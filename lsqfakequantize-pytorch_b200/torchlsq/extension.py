@@ -28,6 +28,10 @@ def _has_ops():
 
 
 _DT = {torch.float32: _cabi.F32, torch.float16: _cabi.F16, torch.bfloat16: _cabi.BF16}
+# the four backend ops (and plans) also take float64 tensors with float64 scale / shift, like the reference's
+# AT_DISPATCH_FLOATING_TYPES_AND_HALF (lsq_cuda.cu:45); statistics / observer / export stay 16- and 32-bit
+_DT_OPS = dict(_DT)
+_DT_OPS[torch.float64] = _cabi.F64
 _workspaces = {}
 _lib_handle = None   # torch.library.Library must stay alive
 
@@ -84,15 +88,14 @@ def _check_common(x, scale, shift, who_x='input'):
         raise RuntimeError("`scale` tensor must be CUDA tensor")
     if not shift.is_cuda:
         raise RuntimeError("`shift` tensor must be CUDA tensor")
-    if x.dtype not in _DT:
-        raise RuntimeError(f"`{who_x}` must be float32, float16 or bfloat16 on the B200 path, got {x.dtype}")
+    if x.dtype not in _DT_OPS:
+        raise RuntimeError(f"`{who_x}` must be float64, float32, float16 or bfloat16 on the B200 path, got {x.dtype}")
     if scale.dtype != shift.dtype:
         raise RuntimeError("`scale` and `shift` must have the same floating-point type")
-    # reference: scale/shift dtype == x dtype (lsq_cuda.cu:34-35); superset: fp32 params with any x
-    if scale.dtype != x.dtype and scale.dtype != torch.float32:
-        raise RuntimeError(f"`{who_x}` and `scale` must have the same floating-point type (or float32 scale/shift)")
-    if x.dtype == torch.float32 and scale.dtype != torch.float32:
-        raise RuntimeError(f"`{who_x}` and `scale` must have the same floating-point type")
+    # reference: scale/shift dtype == x dtype (lsq_cuda.cu:34-35); superset: fp32 params with fp16 / bf16 x
+    if scale.dtype != x.dtype and (scale.dtype != torch.float32 or x.dtype == torch.float64):
+        raise RuntimeError(f"`{who_x}` and `scale` must have the same floating-point type"
+                           + ("" if x.dtype == torch.float64 else " (or float32 scale/shift)"))
 
 
 def _match_layout(grad, xd):
@@ -122,7 +125,7 @@ def _fwd_tensor_cuda(x, scale, shift, quant_min, quant_max, type_min, type_max,
     q = _cabi.qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
     with torch.cuda.device(x.device):
         rc = lib.lsqb200_fwd_tensor(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), n,
-                                    _DT[x.dtype], _DT[scale.dtype], q, _stream_ptr(x.device))
+                                    _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
     _cabi.check(rc, "lsq_forward_per_tensor")
     return y
 
@@ -145,7 +148,7 @@ def _bwd_tensor_cuda(grad, x, scale, shift, quant_min, quant_max, type_min, type
         sp = _stream_ptr(x.device)
         ws = _workspace(x.device, sp)
         rc = lib.lsqb200_bwd_tensor(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                    gscale.data_ptr(), gshift.data_ptr(), n, _DT[x.dtype], _DT[scale.dtype], q,
+                                    gscale.data_ptr(), gshift.data_ptr(), n, _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q,
                                     ws.data_ptr(), ws.numel(), sp)
     _cabi.check(rc, "lsq_backward_per_tensor")
     return gx, gscale, gshift
@@ -176,7 +179,7 @@ def _fwd_channel_cuda(x, scale, shift, axis, quant_min, quant_max, type_min, typ
     q = _cabi.qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
     with torch.cuda.device(x.device):
         rc = lib.lsqb200_fwd_channel(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
-                                     _DT[x.dtype], _DT[scale.dtype], q, _stream_ptr(x.device))
+                                     _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
     _cabi.check(rc, "lsq_forward_per_channel")
     return y
 
@@ -200,8 +203,8 @@ def _bwd_channel_cuda(grad, x, scale, shift, axis, quant_min, quant_max, type_mi
         sp = _stream_ptr(x.device)
         ws = _workspace(x.device, sp)
         rc = lib.lsqb200_bwd_channel(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                     gscale.data_ptr(), gshift.data_ptr(), outer, C, inner, _DT[x.dtype],
-                                     _DT[scale.dtype], q, ws.data_ptr(), ws.numel(), sp)
+                                     gscale.data_ptr(), gshift.data_ptr(), outer, C, inner, _DT_OPS[x.dtype],
+                                     _DT_OPS[scale.dtype], q, ws.data_ptr(), ws.numel(), sp)
     _cabi.check(rc, "lsq_backward_per_channel")
     return gx, gscale, gshift
 

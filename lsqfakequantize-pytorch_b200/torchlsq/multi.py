@@ -17,7 +17,7 @@ from typing import List, Optional
 import torch
 
 from . import _cabi
-from .extension import _DT, _dense_layout
+from .extension import _DT_OPS as _DT, _dense_layout
 
 
 @dataclass
@@ -63,7 +63,7 @@ class LSQPlan:
             for t in (s.x, s.scale, s.shift):
                 if not t.is_cuda or t.device != dev:
                     raise RuntimeError("all plan tensors must live on one CUDA device")
-            if s.x.dtype not in _DT or s.scale.dtype not in _DT:
+            if s.x.dtype not in _DT or s.scale.dtype not in _DT or (s.x.dtype == torch.float64) != (s.scale.dtype == torch.float64):
                 raise RuntimeError(f"unsupported dtype in plan site {i}")
             xd, outer, C, inner = _dense_layout(s.x, s.axis if s.is_perchannel else None)
             if xd.data_ptr() != s.x.data_ptr():

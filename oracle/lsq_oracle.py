@@ -45,6 +45,9 @@ def lib():
                                             c_int, POINTER(Cfg)]
         _lib.lsq_oracle_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(Cfg)]
+        _lib.lsq_oracle_forward_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(Cfg)]
+        _lib.lsq_oracle_backward_f64.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(Cfg)]
         _lib.lsq_oracle_weight_init.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64]
         _lib.lsq_oracle_qparams.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64]
         _lib.lsq_oracle_quantize.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
@@ -96,8 +99,24 @@ def _params(scale, shift):
     return s, b
 
 
+def _params64(scale, shift):
+    s = np.ascontiguousarray(np.asarray(scale, dtype=np.float64).reshape(-1))
+    b = np.ascontiguousarray(np.asarray(shift, dtype=np.float64).reshape(-1))
+    return s, b
+
+
 def forward(x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None):
-    """y with x's dtype / bit pattern.  x is viewed as contiguous (outer, C, inner)."""
+    """y with x's dtype / bit pattern.  x is viewed as contiguous (outer, C, inner).
+    float64 x: float64 scale / shift; c.contract == CONTRACT_CPU restates the reference CPU build (all double),
+    anything else the reference CUDA build (clamps through float, fused v and d)."""
+    if x.dtype == np.float64:
+        xr = np.ascontiguousarray(x)
+        inner = xr.size // (outer * C) if inner is None else inner
+        assert outer * C * inner == xr.size
+        s, b = _params64(scale, shift)
+        y = np.empty_like(xr)
+        lib().lsq_oracle_forward_f64(_p(xr), _p(y), _p(s), _p(b), outer, C, inner, int(per_channel), ctypes.byref(c))
+        return y
     dt = _dt_of(x, dt)
     xr = _raw(x)
     inner = xr.size // (outer * C) if inner is None else inner
@@ -111,7 +130,20 @@ def forward(x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False
 def backward(g, x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None, with_abs=False):
     """(gx, gscale float64[C|1], gshift float64[C|1]): gx in x's dtype; the sums are the exact
     (double) sums of the reference's fp32 per-element terms.  with_abs=True appends the sums of
-    |terms| (x |gs|), the natural yardstick for the error of any fp32 summation order."""
+    |terms| (x |gs|), the natural yardstick for the error of any fp32 summation order.
+    float64 x: the reference's double terms summed in long double."""
+    if x.dtype == np.float64:
+        xr, gr = np.ascontiguousarray(x), np.ascontiguousarray(g, dtype=np.float64)
+        inner = xr.size // (outer * C) if inner is None else inner
+        assert outer * C * inner == xr.size == gr.size
+        s, b = _params64(scale, shift)
+        nslot = C if per_channel else 1
+        gx = np.empty_like(xr)
+        gs_, gb_ = np.zeros(nslot, np.float64), np.zeros(nslot, np.float64)
+        as_, ab_ = np.zeros(nslot, np.float64), np.zeros(nslot, np.float64)
+        lib().lsq_oracle_backward_f64(_p(gr), _p(xr), _p(gx), _p(s), _p(b), _p(gs_), _p(gb_), _p(as_), _p(ab_),
+                                      outer, C, inner, int(per_channel), ctypes.byref(c))
+        return (gx, gs_, gb_, as_, ab_) if with_abs else (gx, gs_, gb_)
     dt = _dt_of(x, dt)
     xr, gr = _raw(x), _raw(g)
     inner = xr.size // (outer * C) if inner is None else inner

@@ -162,3 +162,66 @@ def test_16bit_conversions_match_numpy():
     tb = torch.from_numpy(f).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     mine_b = np.array([lib.lsq_oracle_f2bf(float(v)) for v in f], np.uint16)
     assert np.array_equal(mine_b, tb)
+
+
+# ---- float64 tensors: oracle (contract=0, all double) vs the reference CPU op on float64 ------------------------
+@pytest.fixture(scope="module")
+def golden_f64():
+    import json
+    from pathlib import Path
+    z = np.load(Path(__file__).resolve().parent / "golden" / "ref_cpu_ops_f64.npz")
+    meta = json.loads(str(z["meta"]))
+    return {name: dict(meta=m, **{k: z[f"{name}/{k}"] for k in ("x", "g", "scale", "shift", "y", "dx", "ds", "db")})
+            for name, m in meta.items()}
+
+
+def _same_bits64(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+    na, nb = np.isnan(a), np.isnan(b)
+    return bool(np.array_equal(na, nb) and np.array_equal(a[~na].view(np.uint64), b[~nb].view(np.uint64)))
+
+
+def test_f64_forward_and_grad_x_bit_exact_vs_reference_cpu(golden_f64):
+    assert len(golden_f64) >= 19
+    for name, c in golden_f64.items():
+        m = c["meta"]
+        outer, C, inner = _geom(m)
+        y = O.forward(c["x"], c["scale"], c["shift"], _cfg(m), outer, C, inner, m["per_channel"])
+        assert y.dtype == np.float64 and _same_bits64(y, c["y"]), name
+        gx, _, _ = O.backward(c["g"], c["x"], c["scale"], c["shift"], _cfg(m), outer, C, inner, m["per_channel"])
+        assert _same_bits64(gx, c["dx"]), name
+
+
+def test_f64_param_grads_vs_reference_cpu(golden_f64):
+    """at::sum in double (order unpinned) vs the long-double sum of the same double terms: 1e-13 of sum|terms|."""
+    for name, c in golden_f64.items():
+        m = c["meta"]
+        if np.isnan(c["ds"]).any() or np.isnan(c["db"]).any():
+            continue
+        outer, C, inner = _geom(m)
+        _, gs, gb, a_s, a_b = O.backward(c["g"], c["x"], c["scale"], c["shift"], _cfg(m), outer, C, inner,
+                                         m["per_channel"], with_abs=True)
+        for mine, ref, mag, what in ((gs, c["ds"], a_s, "ds"), (gb, c["db"], a_b, "db")):
+            assert np.all(np.abs(mine - ref) <= 1e-13 * mag + 1e-300), (name, what, mine, ref)
+
+
+def test_f64_cuda_contract_rounds_clamps_through_float(golden_f64):
+    """The CUDA build's float64 arithmetic (::fminf / ::fmaxf on doubles, global_scope.h:51-52): same integers
+    as the CPU build except within a float ulp of a rounding tie, per-channel scales rounded to float."""
+    c = golden_f64["R_tensor_affine"]
+    m = c["meta"]
+    y0 = O.forward(c["x"], c["scale"], c["shift"], _cfg(m), 1, 1, c["x"].size, False)
+    y3 = O.forward(c["x"], c["scale"], c["shift"], _cfg(m, contract=O.CONTRACT_CUDA), 1, 1, c["x"].size, False)
+    step = abs(float(c["scale"][0]))
+    d = np.abs(y0 - y3)
+    assert np.all((d == 0) | (np.abs(d - step) < 1e-12)) and (d != 0).mean() < 1e-3
+    # per-channel: the CUDA build quantises with float(scale)
+    c = golden_f64["R_channel_axis1"]
+    m = c["meta"]
+    outer, C, inner = _geom(m)
+    s32 = c["scale"].astype(np.float32).astype(np.float64)
+    assert np.any(s32 != c["scale"])
+    y_cuda = O.forward(c["x"], c["scale"], c["shift"], _cfg(m, contract=O.CONTRACT_CUDA), outer, C, inner, True)
+    y_cpu_f32scale = O.forward(c["x"], s32, c["shift"], _cfg(m), outer, C, inner, True)
+    assert np.mean(y_cuda == y_cpu_f32scale) > 0.99
