@@ -1,5 +1,6 @@
 // kern_col.cu -- instantiations of the column-layout (short channel rows) kernels.
-// Variants (unit words, rows in flight, min CTAs/SM fwd / bwd): 0 = (4, 2, 4/2), 1 = (4, 4, 3/2), 2 = (2, 4, 6/4), 3 = (2, 8, 4/3)
+// Variants (unit words, rows in flight, min CTAs/SM fwd / bwd): 0 = (4, 2, 4/3), 1 = (4, 4, 3/2), 2 = (2, 4, 6/4), 3 = (2, 8, 4/3),
+// 4 = (4, 2, 6/4), 5 = (4, 1, 6/4)
 #include "lsq_column.cuh"
 #include "lsq_host.h"
 namespace lsqb200 {
@@ -24,7 +25,9 @@ ColKernelFn pick_f(bool init, int v) {
         case 1: return V<T, MODE, 4, 4, 3, 2>::f(init);
         case 2: return V<T, MODE, 2, 4, 6, 4>::f(init);
         case 3: return V<T, MODE, 2, 8, 4, 3>::f(init);
-        default: return V<T, MODE, 4, 2, 4, 2>::f(init);
+        case 4: return V<T, MODE, 4, 2, 6, 4>::f(init);
+        case 5: return V<T, MODE, 4, 1, 6, 4>::f(init);
+        default: return V<T, MODE, 4, 2, 4, 3>::f(init);
     }
 }
 template <typename T, int MODE>
@@ -33,7 +36,9 @@ ColKernelFn pick_b(int bmode, int v) {
         case 1: return V<T, MODE, 4, 4, 3, 2>::b(bmode);
         case 2: return V<T, MODE, 2, 4, 6, 4>::b(bmode);
         case 3: return V<T, MODE, 2, 8, 4, 3>::b(bmode);
-        default: return V<T, MODE, 4, 2, 4, 2>::b(bmode);
+        case 4: return V<T, MODE, 4, 2, 6, 4>::b(bmode);
+        case 5: return V<T, MODE, 4, 1, 6, 4>::b(bmode);
+        default: return V<T, MODE, 4, 2, 4, 3>::b(bmode);
     }
 }
 }  // namespace

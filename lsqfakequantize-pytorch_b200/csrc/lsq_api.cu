@@ -118,7 +118,7 @@ int occupancy_of(const void* fn, int threads) {
     return occ;
 }
 
-ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_bytes, const Tuning& tn, int occ) {
+ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_bytes, const Tuning& tn, int occ, bool backward) {
     ColGeom g{};
     const int ub = kColVariantNW[tn.col_variant] * 4;
     const int es = elem_size(xdt), vec = ub / es;
@@ -134,7 +134,8 @@ ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_
     // whole waves of CTAs (col_waves per resident slot); the per-thread set-up (2*VEC parameter loads,
     // VEC divisions) is amortised over every row a thread visits
     const long long slots = (long long)tn.sm_count * occ;
-    long long splits = ((long long)tn.col_waves * slots + g.col_blocks - 1) / g.col_blocks;
+    // round DOWN: col_blocks * splits must not spill into a partly filled extra wave (686 CTAs on 2 x 296 slots ran 3 waves)
+    long long splits = ((long long)(backward ? tn.col_waves_bwd : tn.col_waves) * slots) / g.col_blocks;
     if (splits < 1) splits = 1;
     long long rows_pt = (outer + splits * g.ty - 1) / (splits * g.ty);
     if (rows_pt < 2) rows_pt = 2;
@@ -189,7 +190,7 @@ int forward_common(const void* x, void* y, const void* scale, const void* shift,
     if (xdt == DT_F64 && common_alignment({x, y, scale, shift}) < 8) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
     if (per_channel && xdt != DT_F64) {
         ColKernelFn ck = get_col_fwd_kernel(xdt, mode, q->init_mode != 0, tuning().col_variant);
-        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, y}), tuning(), occupancy_of((const void*)ck, kColThreads));
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, y}), tuning(), occupancy_of((const void*)ck, kColThreads), false);
         if (cg.ok) {
             const ColSeg cs = make_colseg(cg, x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, pdt, q, nullptr);
             return launch_col(ck, cs, cg, (cudaStream_t)stream);
@@ -226,7 +227,7 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
         return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
     if (per_channel && xdt != DT_F64) {
         ColKernelFn ck = get_col_bwd_kernel(xdt, mode, bmode_of(q), tuning().col_variant);
-        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads));
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads), true);
         if (cg.ok) {
             if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
                 return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
@@ -434,6 +435,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "column_path") g_tuning.column_path = v;
         else if (k == "col_variant") g_tuning.col_variant = (v >= 0 && v < kColVariants) ? v : 0;
         else if (k == "col_waves") g_tuning.col_waves = v > 0 ? v : 2;
+        else if (k == "col_waves_bwd") g_tuning.col_waves_bwd = v > 0 ? v : 1;
         else if (k == "column_max_row_bytes") g_tuning.column_max_row_bytes = v;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;

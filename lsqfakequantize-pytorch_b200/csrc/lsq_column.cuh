@@ -51,7 +51,6 @@ template <typename T, int MODE, int CNW>
 struct SlotParams {
     static constexpr int VEC = ColVec<T, CNW>::VEC;
     float s[VEC], inv_s[VEC], zp[VEC];
-    int ch[VEC];
     __device__ __forceinline__ void load(const ColSeg& cs, long long unit_col) {
         Seg fake;                       // make_chan only reads these fields
         fake.per_channel = 1; fake.tmin = cs.tmin; fake.tmax = cs.tmax; fake.qmin = cs.qmin; fake.qmax = cs.qmax;
@@ -61,7 +60,6 @@ struct SlotParams {
         float sraw[VEC], braw[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; k++) {          // issue every parameter load before the first use
-            ch[k] = (int)c;
             sraw[k] = load_param(cs.scale, c, cs.pdt);
             braw[k] = load_param(cs.shift, c, cs.pdt);
             if (++r == inner) { r = 0; ++c; }
@@ -80,120 +78,148 @@ struct SlotParams {
     }
 };
 
+// rows this thread visits inside its row split, and the byte offset of the first one (ty is a power of two)
+struct ColWalk {
+    long long off, stride;   // bytes
+    int cnt;
+    __device__ __forceinline__ void init(const ColSeg& cs, long long uc, int ty, int ub) {
+        const long long n0 = (long long)blockIdx.y * cs.rows_per_split + ty;
+        long long n_end = ((long long)blockIdx.y + 1) * cs.rows_per_split;
+        if (n_end > cs.outer) n_end = cs.outer;
+        const int sh = __ffs(cs.ty) - 1;
+        cnt = n0 < n_end ? (int)((unsigned)(n_end - n0 + cs.ty - 1) >> sh) : 0;    // rows_per_split < 2^31
+        off = (n0 * cs.units_per_row + uc) * ub;
+        stride = ((long long)cs.units_per_row << sh) * ub;
+    }
+};
+
 template <typename T, int MODE, bool INIT, int CNW, int kColUnroll, int MINB, int LD, int ST>
 __global__ void __launch_bounds__(kColThreads, MINB)
 lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
     constexpr int NW = CNW, VEC = ColVec<T, CNW>::VEC, UB = CNW * 4;
     asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tx = threadIdx.x % cs.tx, ty = threadIdx.x / cs.tx;
     const long long uc = (long long)blockIdx.x * cs.tx + tx;
     if (uc >= cs.units_per_row) return;
-    const char* __restrict__ xp = reinterpret_cast<const char*>(cs.x);
-    char* __restrict__ yp = reinterpret_cast<char*>(cs.y);
+    ColWalk w;
+    w.init(cs, uc, ty, UB);
+    const char* __restrict__ px = reinterpret_cast<const char*>(cs.x) + w.off;
+    char* __restrict__ py = reinterpret_cast<char*>(cs.y) + w.off;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     SlotParams<T, MODE, CNW> sp;
     if (!INIT) sp.load(cs, uc);
-    long long n = (long long)blockIdx.y * cs.rows_per_split + ty;
-    long long n_end = ((long long)blockIdx.y + 1) * cs.rows_per_split;
-    if (n_end > cs.outer) n_end = cs.outer;
-    for (; n < n_end; n += (long long)cs.ty * kColUnroll) {
+    int cnt = w.cnt;
+    // whole groups of kColUnroll rows: unconditional loads and stores
+    for (; cnt >= kColUnroll; cnt -= kColUnroll) {
         Raw<NW> xr[kColUnroll];
-        long long a[kColUnroll];
+#pragma unroll
+        for (int r = 0; r < kColUnroll; r++) xr[r] = ld_unit<LD, NW>(px + r * w.stride);
 #pragma unroll
         for (int r = 0; r < kColUnroll; r++) {
-            const long long nn = n + (long long)r * cs.ty;
-            a[r] = (nn < n_end ? nn : n) * cs.units_per_row + uc;
-            xr[r] = ld_unit<LD, NW>(xp + a[r] * UB);
-        }
-#pragma unroll
-        for (int r = 0; r < kColUnroll; r++) {
-            if (n + (long long)r * cs.ty >= n_end) continue;
-            if (INIT) { st_unit<ST, NW>(yp + a[r] * UB, xr[r]); continue; }
+            if (INIT) { st_unit<ST, NW>(py + r * w.stride, xr[r]); continue; }
             float f[VEC];
             unpack_unit<T, NW>(xr[r], f);
 #pragma unroll
             for (int k = 0; k < VEC; k++) f[k] = fq_forward<MODE>(f[k], sp.chan(k, cs));
-            st_unit<ST, NW>(yp + a[r] * UB, pack_unit<T, NW>(f));
+            st_unit<ST, NW>(py + r * w.stride, pack_unit<T, NW>(f));
         }
+        px += kColUnroll * w.stride; py += kColUnroll * w.stride;
+    }
+    for (; cnt > 0; cnt--) {
+        const Raw<NW> xr = ld_unit<LD, NW>(px);
+        if (INIT) st_unit<ST, NW>(py, xr);
+        else {
+            float f[VEC];
+            unpack_unit<T, NW>(xr, f);
+#pragma unroll
+            for (int k = 0; k < VEC; k++) f[k] = fq_forward<MODE>(f[k], sp.chan(k, cs));
+            st_unit<ST, NW>(py, pack_unit<T, NW>(f));
+        }
+        px += w.stride; py += w.stride;
     }
 }
 
+// A channel here sums outer*inner >= thousands of terms, so the column backward uses the streaming form of
+// fq_backward (fused accumulation, lsq_device.cuh) like the row-tiled kernels do for long channels.
 template <typename T, int MODE, int BMODE, int CNW, int kColUnroll, int MINB, int LD, int ST>
 __global__ void __launch_bounds__(kColThreads, MINB)
 lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
     constexpr int NW = CNW, VEC = ColVec<T, CNW>::VEC, UB = CNW * 4;
-    constexpr int FLUSH_ITERS = 32 / kColUnroll;             // promote fp32 partials to fp64 every 32 rows
+    constexpr int FLUSH_ROWS = 32;                            // promote fp32 partials to fp64 every 32 rows
     // private fp64 accumulators of every thread's element slots, [S|B][slot][thread]: no atomics, no conflicts
     __shared__ double sacc[2][VEC][kColThreads];
     __shared__ int last_flag;
     asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int tx = threadIdx.x % cs.tx, ty = threadIdx.x / cs.tx;
     const long long uc = (long long)blockIdx.x * cs.tx + tx;
     const bool active = uc < cs.units_per_row;
-    const char* __restrict__ xp = reinterpret_cast<const char*>(cs.x);
-    const char* __restrict__ gp = reinterpret_cast<const char*>(cs.g);
-    char* __restrict__ gxp = reinterpret_cast<char*>(cs.gx);
-    const bool write_gx = gxp != nullptr;
     float accS[VEC], accB[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; k++) { accS[k] = 0.f; accB[k] = 0.f; sacc[0][k][threadIdx.x] = 0.0; sacc[1][k][threadIdx.x] = 0.0; }
-    SlotParams<T, MODE, CNW> sp;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (active) {
+        ColWalk w;
+        w.init(cs, uc, ty, UB);
+        const char* __restrict__ px = reinterpret_cast<const char*>(cs.x) + w.off;
+        const char* __restrict__ pg = reinterpret_cast<const char*>(cs.g) + w.off;
+        char* __restrict__ pgx = cs.gx ? reinterpret_cast<char*>(cs.gx) + w.off : nullptr;
+        SlotParams<T, MODE, CNW> sp;
         sp.load(cs, uc);
-        long long n = (long long)blockIdx.y * cs.rows_per_split + ty;
-        long long n_end = ((long long)blockIdx.y + 1) * cs.rows_per_split;
-        if (n_end > cs.outer) n_end = cs.outer;
-        int since_flush = 0;
-        for (; n < n_end; n += (long long)cs.ty * kColUnroll) {
+        auto flush = [&]() {
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                sacc[0][k][threadIdx.x] += (double)accS[k]; accS[k] = 0.f;
+                sacc[1][k][threadIdx.x] += (double)accB[k]; accB[k] = 0.f;
+            }
+        };
+        auto row = [&](const Raw<NW>& xr, const Raw<NW>& gr, char* dst) {
+            float fx[VEC], fg[VEC];
+            unpack_unit<T, NW>(xr, fx);
+            unpack_unit<T, NW>(gr, fg);
+#pragma unroll
+            for (int k = 0; k < VEC; k++)
+                fg[k] = fq_backward<MODE, BMODE, false>(fg[k], fx[k], sp.chan(k, cs), accS[k], accB[k]);
+            if (dst) {
+                if (bmode_passthrough(BMODE)) st_unit<ST, NW>(dst, gr);
+                else st_unit<ST, NW>(dst, pack_unit<T, NW>(fg));
+            }
+        };
+        int cnt = w.cnt, since = 0;
+        for (; cnt >= kColUnroll; cnt -= kColUnroll) {
             Raw<NW> xr[kColUnroll], gr[kColUnroll];
-            long long a[kColUnroll];
 #pragma unroll
             for (int r = 0; r < kColUnroll; r++) {
-                const long long nn = n + (long long)r * cs.ty;
-                a[r] = (nn < n_end ? nn : n) * cs.units_per_row + uc;
-                xr[r] = ld_unit<LD, NW>(xp + a[r] * UB);
-                gr[r] = ld_unit<LD, NW>(gp + a[r] * UB);
+                xr[r] = ld_unit<LD, NW>(px + r * w.stride);
+                gr[r] = ld_unit<LD, NW>(pg + r * w.stride);
             }
 #pragma unroll
-            for (int r = 0; r < kColUnroll; r++) {
-                if (n + (long long)r * cs.ty >= n_end) continue;
-                float fx[VEC], fg[VEC];
-                unpack_unit<T, NW>(xr[r], fx);
-                unpack_unit<T, NW>(gr[r], fg);
-#pragma unroll
-                for (int k = 0; k < VEC; k++)
-                    fg[k] = fq_backward<MODE, BMODE, true>(fg[k], fx[k], sp.chan(k, cs), accS[k], accB[k]);
-                if (write_gx) {
-                    if (bmode_passthrough(BMODE)) st_unit<ST, NW>(gxp + a[r] * UB, gr[r]);
-                    else st_unit<ST, NW>(gxp + a[r] * UB, pack_unit<T, NW>(fg));
-                }
-            }
-            if (bmode_reduces(BMODE) && ++since_flush == FLUSH_ITERS) {
-                since_flush = 0;
-#pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    sacc[0][k][threadIdx.x] += (double)accS[k]; accS[k] = 0.f;
-                    sacc[1][k][threadIdx.x] += (double)accB[k]; accB[k] = 0.f;
-                }
-            }
+            for (int r = 0; r < kColUnroll; r++) row(xr[r], gr[r], pgx ? pgx + r * w.stride : nullptr);
+            px += kColUnroll * w.stride; pg += kColUnroll * w.stride;
+            if (pgx) pgx += kColUnroll * w.stride;
+            if (bmode_reduces(BMODE) && (since += kColUnroll) >= FLUSH_ROWS) { since = 0; flush(); }
         }
+        for (; cnt > 0; cnt--) {
+            const Raw<NW> xr = ld_unit<LD, NW>(px), gr = ld_unit<LD, NW>(pg);
+            row(xr, gr, pgx);
+            px += w.stride; pg += w.stride;
+            if (pgx) pgx += w.stride;
+        }
+        if (bmode_reduces(BMODE)) flush();
     }
+    // channel of element slot k of this thread's column unit (L = C*inner < 2^31, checked on the host)
+    auto slot_channel = [&](int k) { return (int)(((unsigned)uc * VEC + (unsigned)k) / (unsigned)cs.inner); };
     if constexpr (!bmode_reduces(BMODE)) {      // eval: exact zeros, written by the first row-split
         if (active && blockIdx.y == 0 && ty == 0) {
 #pragma unroll
-            for (int k = 0; k < VEC; k++)
-                if (k == 0 || sp.ch[k] != sp.ch[k > 0 ? k - 1 : 0]) {
-                    store_param(cs.gscale, sp.ch[k], cs.pdt, 0.0);
-                    store_param(cs.gshift, sp.ch[k], cs.pdt, 0.0);
+            for (int k = 0; k < VEC; k++) {
+                const int c = slot_channel(k);
+                if (k == 0 || c != slot_channel(k > 0 ? k - 1 : 0)) {
+                    store_param(cs.gscale, c, cs.pdt, 0.0);
+                    store_param(cs.gshift, c, cs.pdt, 0.0);
                 }
+            }
         }
     } else {
-#pragma unroll
-    for (int k = 0; k < VEC; k++) {
-        sacc[0][k][threadIdx.x] += (double)accS[k];
-        sacc[1][k][threadIdx.x] += (double)accB[k];
-    }
     __syncthreads();
     // thread row 0 adds the CTA's thread rows in a fixed order, merges neighbouring slots of the same
     // channel and issues one fp64 atomic pair per channel run
@@ -202,9 +228,10 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
             for (int r = 0; r < cs.ty; r++) { rs += sacc[0][k][r * cs.tx + tx]; rb += sacc[1][k][r * cs.tx + tx]; }
-            if (k == VEC - 1 || sp.ch[k + 1 < VEC ? k + 1 : k] != sp.ch[k]) {
-                atomicAdd(cs.acc + 2 * (long long)sp.ch[k], rs);
-                atomicAdd(cs.acc + 2 * (long long)sp.ch[k] + 1, rb);
+            const int c = slot_channel(k);
+            if (k == VEC - 1 || slot_channel(k + 1 < VEC ? k + 1 : k) != c) {
+                atomicAdd(cs.acc + 2 * (long long)c, rs);
+                atomicAdd(cs.acc + 2 * (long long)c + 1, rb);
                 rs = 0.0; rb = 0.0;
             }
         }
@@ -232,7 +259,7 @@ using ColKernelFn = void (*)(const ColSeg);
 ColKernelFn get_col_fwd_kernel(int xdtype, int mode, bool init, int variant);
 ColKernelFn get_col_bwd_kernel(int xdtype, int mode, int bmode, int variant);
 // variant -> (unit words, rows in flight, min CTAs/SM); index with Tuning::col_variant
-constexpr int kColVariants = 4;
-constexpr int kColVariantNW[kColVariants] = {4, 4, 2, 2};
+constexpr int kColVariants = 6;
+constexpr int kColVariantNW[kColVariants] = {4, 4, 2, 2, 4, 4};
 
 }  // namespace lsqb200

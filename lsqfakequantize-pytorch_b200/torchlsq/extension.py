@@ -216,6 +216,26 @@ def _no_cpu(name):
     return impl
 
 
+# ---- shape functions (dispatch key Meta): meta / fake tensors flow through the ops, so models can be built on
+#      device='meta' and traced for shapes; no arithmetic happens here and nothing falls back to it ---------------
+def _fwd_meta(x, scale, shift, *scalars):
+    return torch.empty_like(x)
+
+
+def _bwd_tensor_meta(grad, x, scale, shift, *scalars):
+    return torch.empty_like(x), scale.new_empty(1), shift.new_empty(1)
+
+
+def _bwd_channel_meta(grad, x, scale, shift, axis, *scalars):
+    _check_channel(x, scale, shift, axis)
+    return torch.empty_like(x), scale.new_empty(x.shape[axis]), shift.new_empty(x.shape[axis])
+
+
+def _fwd_channel_meta(x, scale, shift, axis, *scalars):
+    _check_channel(x, scale, shift, axis)
+    return torch.empty_like(x)
+
+
 # ---- autograd layer (replaces csrc/ops/autograd/lsq_autograd.cpp:16-210) -------------------------
 class _LSQPerTensorBackwardFunction(torch.autograd.Function):
     @staticmethod
@@ -318,6 +338,9 @@ def _register_extensions():
                      ("lsq_forward_per_channel", _fwd_channel_cuda), ("lsq_backward_per_channel", _bwd_channel_cuda)):
         L.impl(name, fn, "CUDA")
         L.impl(name, _no_cpu(name), "CPU")
+    for name, fn in (("lsq_forward_per_tensor", _fwd_meta), ("lsq_backward_per_tensor", _bwd_tensor_meta),
+                     ("lsq_forward_per_channel", _fwd_channel_meta), ("lsq_backward_per_channel", _bwd_channel_meta)):
+        L.impl(name, fn, "Meta")
     L.impl("lsq_forward_per_tensor", lambda *a: _LSQPerTensorFunction.apply(*a), "Autograd")
     L.impl("lsq_backward_per_tensor", lambda *a: _LSQPerTensorBackwardFunction.apply(*a), "Autograd")
     L.impl("lsq_forward_per_channel", lambda *a: _LSQPerChannelFunction.apply(*a), "Autograd")

@@ -157,7 +157,8 @@ def test_errors_match_reference_behaviour():
     with pytest.raises(RuntimeError, match="same floating-point type"):
         lsq(x, s.half(), b.half())
     with pytest.raises(RuntimeError, match="float32, float16 or bfloat16"):
-        lsq(x.double(), s.double(), b.double())
+        lsq(x.to(torch.int32), s, b)
+    assert lsq(x.double(), s.double(), b.double()).dtype == torch.float64      # float64 is served (tests/test_gpu_f64.py)
     with pytest.raises(RuntimeError, match="not consistent"):
         lsq(x, torch.ones(5, device=U.DEV), torch.zeros(5, device=U.DEV), is_perchannel=True, axis=1)
     with pytest.raises(RuntimeError, match="axis"):

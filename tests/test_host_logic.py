@@ -208,3 +208,25 @@ def test_observer_mode_copies_observer_qparams(monkeypatch, golden_module):
     assert len(seen) == len(ref)
     for (s, b), r in zip(seen, ref):
         assert s == pytest.approx(r["scale"], rel=1e-6) and b == pytest.approx(r["shift"], rel=1e-6, abs=1e-7)
+
+
+def test_meta_tensors_flow_through_the_ops():
+    """Shape functions only (dispatch key Meta): same shapes / strides / dtypes as the CUDA kernels produce."""
+    import torch
+    import torchlsq  # noqa: F401
+    x = torch.empty(4, 6, 5, 5, device="meta").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    s = torch.empty(1, device="meta", requires_grad=True)
+    b = torch.empty(1, device="meta", requires_grad=True)
+    y = torch.ops.torchlsq.lsq(x, s, b, 0, 127, 0, 255, 1, True, 1.0, True, False, False, False)
+    assert y.is_meta and y.shape == x.shape and y.stride() == x.stride()
+    y.backward(torch.empty_like(y))
+    assert x.grad.shape == x.shape and s.grad.shape == (1,) and b.grad.shape == (1,)
+    sc = torch.empty(6, device="meta", requires_grad=True)
+    bc = torch.empty(6, device="meta", requires_grad=True)
+    yc = torch.ops.torchlsq.lsq(x.detach(), sc, bc, 0, 127, 0, 255, 1, True, 1.0, True, True, False, False)
+    yc.backward(torch.empty_like(yc))
+    assert sc.grad.shape == (6,) and bc.grad.shape == (6,)
+    import pytest
+    with pytest.raises(RuntimeError, match="not consistent"):
+        torch.ops.torchlsq.lsq(x.detach(), torch.empty(5, device="meta"), torch.empty(5, device="meta"), 0, 127, 0, 255, 1, True, 1.0,
+                               True, True, False, False)

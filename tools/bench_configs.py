@@ -70,6 +70,11 @@ def main():
         lib.lsqb200_bwd_tensor(g.data_ptr(), x.data_ptr(), gx.data_ptr(), s.data_ptr(), b.data_ptr(), gs.data_ptr(), gb.data_ptr(),
                                n, 0, 0, q, ws.data_ptr(), ws.numel(), sp)
     report("config1_per_tensor_fp32_32x64x56x56_fwd_bwd", 5 * 4 * n, *timed(c1, args.iters, flush), l2="flushed", launches=2)
+    # size-matched ceiling: the same bytes moved by ATen's own streaming kernels (copy = R+W, add = 2R+W), same flush, 2 launches
+    def c1_copy_add():
+        y.copy_(x)
+        torch.add(x, g, out=gx)
+    report("config1_ceiling_aten_copy_plus_add_same_bytes", 5 * 4 * n, *timed(c1_copy_add, args.iters, flush), l2="flushed", launches=2)
     report("config1_same_L2_warm", 5 * 4 * n, *timed(c1, args.iters, None), l2="warm (103 MB working set fits the 126 MB L2)", launches=2)
 
     # ---- config 2: 54 ResNet-50 weights, per-channel axis 0, symmetric qint8, mu+-3sigma init
@@ -92,6 +97,13 @@ def main():
         plan.backward()
     report("config2_weights_fwd_bwd_54_tensors_plan", 5 * 4 * nw, *timed(c2, args.iters, flush), l2="flushed",
            launches=plan.launches(False) + plan.launches(True))
+    fa, fb, fc = (torch.empty(nw, device=DEV).normal_(generator=gen) for _ in range(3))
+
+    def c2_copy_add():
+        fc.copy_(fa)
+        torch.add(fa, fb, out=fc)
+    report("config2_ceiling_aten_copy_plus_add_same_bytes_flat", 5 * 4 * nw, *timed(c2_copy_add, args.iters, flush), l2="flushed", launches=2)
+    report("config2_ceiling_aten_sum_same_bytes_flat", 4 * nw, *timed(lambda: fa.sum(), args.iters, flush), l2="flushed", launches=2)
     qw = _cabi.qargs(-128, 127, -128, 127, True, 1.0, True, False, False)
 
     def c2_per_tensor():

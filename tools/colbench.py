@@ -5,7 +5,7 @@ lib=_cabi.load(); DEV='cuda:0'
 ws=torch.zeros(lib.lsqb200_workspace_bytes(),dtype=torch.uint8,device=DEV)
 sp=torch.cuda.current_stream().cuda_stream
 q=_cabi.qargs(0,127,0,255,True,1.0,False,False,False)
-N=256*1024*784
+N=1024*1024*196
 x=torch.empty(N,dtype=torch.float16,device=DEV).normal_(); g=torch.empty_like(x).normal_(); y=torch.empty_like(x); gx=torch.empty_like(x)
 def run(outer,C,inner,tune):
     lib.lsqb200_set_tuning(tune.encode())
@@ -23,6 +23,6 @@ def run(outer,C,inner,tune):
             if i>=3: ts.append(e0.elapsed_time(e1))
         res.append(round(nb*2*outer*C*inner/statistics.median(ts)/1e6))
     return res
-for shape in ((256*196,1024,1),(256,2048,49),(256,1024,196),(4096,1000,1)):
-    for tune in ("col_variant=0","col_variant=1","col_variant=2","col_variant=3","col_variant=0,col_waves=1","col_variant=2,col_waves=1","col_variant=2,col_waves=4","col_variant=3,col_waves=1","col_variant=3,col_waves=4"):
+for shape in ((256*196,1024,1),(256,2048,49),(256,1024,196),(4096,1000,1),(1024,1024,196)):
+    for tune in ("col_variant=0","col_variant=1","col_variant=2","col_variant=3","col_variant=4","col_variant=5","col_variant=0,col_waves=1","col_variant=1,col_waves=1","col_variant=4,col_waves=1","col_variant=5,col_waves=1","col_variant=1,col_waves=3","col_variant=1,col_waves=4","col_variant=3,col_waves=1","col_variant=3,col_waves=3"):
         print(shape, tune, 'fwd/bwd GB/s', run(*shape,tune), flush=True)
