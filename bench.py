@@ -511,6 +511,22 @@ def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
 
     one_step()
     barrier()
+    # PCIe ceiling of this box for the same traffic shape: the largest site's x, g in and y, gx out as bare copies on two
+    # streams, nothing else running (CUDA events; this is the roofline the end-to-end number is bound by)
+    dummy = ring[0]
+    pe = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    for rep in range(2):
+        pe[0].record(s_in); pe[2].record(s_out)
+        for _ in range(2):
+            with torch.cuda.stream(s_in):
+                dummy["xd"].copy_(xh, non_blocking=True); dummy["gd"].copy_(gh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh.copy_(dummy["xd"], non_blocking=True); gxh.copy_(dummy["gd"], non_blocking=True)
+        pe[1].record(s_in); pe[3].record(s_out)
+        torch.cuda.synchronize()
+    pcie_in = 4 * 2 * nmax / (pe[0].elapsed_time(pe[1]) * 1e-3) / 1e9
+    pcie_out = 4 * 2 * nmax / (pe[2].elapsed_time(pe[3]) * 1e-3) / 1e9
+    barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         one_step()
@@ -524,6 +540,8 @@ def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
     alg = (5 * 2 * sum(sizes) + 5 * 4 * n_w) * world
     return {"value": round(alg / dt / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": steps, "ms_per_step": round(dt * 1e3, 2), "pcie_GBps_each_way": round(h2d / dt / 1e9, 1),
+            "pcie_ceiling_GBps": {"h2d": round(pcie_in, 1), "d2h": round(pcie_out, 1),
+                                  "how": "bare pinned<->device copies of the largest site, both directions at once, CUDA events"},
             "path": "pinned host x,g -> torchlsq.functional.lsq + autograd (copy-in / compute / copy-out streams) -> pinned host y,gx,grads; weights stay on device"}
 
 

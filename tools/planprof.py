@@ -15,3 +15,7 @@ flush=torch.empty(512<<20,dtype=torch.uint8,device=DEV)
 for i in range(3):
     flush.fill_(i); plan.forward(); plan.backward()
 torch.cuda.synchronize()
+scales = torch.empty(plan.num_param_slots, device=DEV)
+for i in range(2):
+    flush.fill_(i); plan.weight_init_stats(scales)
+torch.cuda.synchronize()

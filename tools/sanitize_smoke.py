@@ -29,6 +29,37 @@ for dt in (torch.float32, torch.bfloat16, torch.float16):
         check(x, g, s, b, U.qa(), outer, C, inner, True)
 xh = torch.randn(20_001, generator=gen).half().to(U.DEV); gh = torch.randn(20_001, generator=gen).half().to(U.DEV)
 check(xh, gh, torch.tensor([0.03], device=U.DEV).half(), torch.tensor([-1.7], device=U.DEV).half(), U.qa(use_gs=False))
+# float64 kernels (lsq_f64.cuh): per-tensor (peel, single tile, split tiles) and per-channel rows / strided rows
+from oracle import lsq_oracle as O
+from torchlsq import _cabi
+lib = _cabi.load()
+def check64(x, g, s, b, q, outer=1, C=1, inner=None, pc=False):
+    inner = x.numel() // (outer * C) if inner is None else inner
+    y, gx = torch.empty_like(x), torch.empty_like(x)
+    n = C if pc else 1
+    gs = torch.empty(n, dtype=torch.float64, device=U.DEV); gb = torch.empty(n, dtype=torch.float64, device=U.DEV)
+    ws = U.workspace()
+    if pc:
+        assert lib.lsqb200_fwd_channel(x.data_ptr(), y.data_ptr(), s.data_ptr(), b.data_ptr(), outer, C, inner, 3, 3, q, U.stream()) == 0
+        assert lib.lsqb200_bwd_channel(g.data_ptr(), x.data_ptr(), gx.data_ptr(), s.data_ptr(), b.data_ptr(), gs.data_ptr(), gb.data_ptr(),
+                                       outer, C, inner, 3, 3, q, ws.data_ptr(), ws.numel(), U.stream()) == 0
+    else:
+        assert lib.lsqb200_fwd_tensor(x.data_ptr(), y.data_ptr(), s.data_ptr(), b.data_ptr(), x.numel(), 3, 3, q, U.stream()) == 0
+        assert lib.lsqb200_bwd_tensor(g.data_ptr(), x.data_ptr(), gx.data_ptr(), s.data_ptr(), b.data_ptr(), gs.data_ptr(), gb.data_ptr(),
+                                      x.numel(), 3, 3, q, ws.data_ptr(), ws.numel(), U.stream()) == 0
+    cfg = U.ocfg(q)
+    oy = O.forward(x.cpu().numpy().reshape(-1), s.cpu().numpy(), b.cpu().numpy(), cfg, outer, C, inner, pc)
+    ogx, ogs, ogb = O.backward(g.cpu().numpy().reshape(-1), x.cpu().numpy().reshape(-1), s.cpu().numpy(), b.cpu().numpy(), cfg, outer, C, inner, pc)
+    assert np.array_equal(y.cpu().numpy().reshape(-1), oy) and np.array_equal(gx.cpu().numpy().reshape(-1), ogx)
+    assert np.allclose(gs.cpu().numpy(), ogs, rtol=1e-9, atol=1e-12)
+for n in (5, 4099, 300_001):
+    x = torch.randn(n, generator=gen, dtype=torch.float64).to(U.DEV); g = torch.randn(n, generator=gen, dtype=torch.float64).to(U.DEV)
+    check64(x, g, torch.tensor([0.03], dtype=torch.float64, device=U.DEV), torch.tensor([-1.7], dtype=torch.float64, device=U.DEV), U.qa())
+for shape, axis in (((64, 3, 7, 7), 0), ((4, 32, 14, 14), 1), ((3, 5, 7), 2)):
+    n = int(np.prod(shape)); outer = int(np.prod(shape[:axis])); C = shape[axis]; inner = n // (outer * C)
+    x = torch.randn(n, generator=gen, dtype=torch.float64).to(U.DEV); g = torch.randn(n, generator=gen, dtype=torch.float64).to(U.DEV)
+    s = (0.02 + 0.02 * torch.rand(C, generator=gen, dtype=torch.float64)).to(U.DEV); b = (-torch.rand(C, generator=gen, dtype=torch.float64)).to(U.DEV)
+    check64(x, g, s, b, U.qa(), outer, C, inner, True)
 sites = []
 for shp in ((16, 3, 7, 7), (32, 16, 1, 1), (8, 8, 3, 3)):
     w = (torch.randn(*shp, generator=gen) * 0.05).to(U.DEV)
