@@ -42,6 +42,30 @@ ColKernelFn pick_b(int bmode, int v) {
     }
 }
 }  // namespace
+namespace {
+template <typename T, int MODE, int R, int S>
+ColKernelFn pick_tma_b(int bmode) {
+    switch (bmode) {
+        case B_NORMAL: return lsq_col_bwd_tma_kernel<T, MODE, B_NORMAL, R, S, kSt>;
+        case B_INIT: return lsq_col_bwd_tma_kernel<T, MODE, B_INIT, R, S, kSt>;
+        case B_EVAL: return lsq_col_bwd_tma_kernel<T, MODE, B_EVAL, R, S, kSt>;
+        default: return lsq_col_bwd_tma_kernel<T, MODE, B_EVAL_INIT, R, S, kSt>;
+    }
+}
+template <typename T, int MODE>
+ColKernelFn pick_tma(int bmode, int tv, int* smem) {
+    switch (tv) {
+        case 2: *smem = 4 * 2 * 2 * kTmaRowBytes; return pick_tma_b<T, MODE, 2, 4>(bmode);
+        case 3: *smem = 3 * 2 * 8 * kTmaRowBytes; return pick_tma_b<T, MODE, 8, 3>(bmode);
+        default: *smem = 3 * 2 * 4 * kTmaRowBytes; return pick_tma_b<T, MODE, 4, 3>(bmode);
+    }
+}
+}  // namespace
+ColKernelFn get_col_bwd_tma_kernel(int xdtype, int mode, int bmode, int tv, int* smem) {
+    if (xdtype == DT_F32) return pick_tma<float, M_FP32>(bmode, tv, smem);
+    if (xdtype == DT_BF16) return pick_tma<__nv_bfloat16, M_FP32>(bmode, tv, smem);
+    return mode == M_HALF_EXACT ? pick_tma<__half, M_HALF_EXACT>(bmode, tv, smem) : pick_tma<__half, M_FP32>(bmode, tv, smem);
+}
 ColKernelFn get_col_fwd_kernel(int xdtype, int mode, bool init, int v) {
     if (xdtype == DT_F32) return pick_f<float, M_FP32>(init, v);
     if (xdtype == DT_BF16) return pick_f<__nv_bfloat16, M_FP32>(init, v);

@@ -163,10 +163,21 @@ ColSeg make_colseg(const ColGeom& g, const void* x, void* y, const void* grad, v
     return cs;
 }
 
-int launch_col(ColKernelFn k, const ColSeg& cs, const ColGeom& g, cudaStream_t st) {
+int launch_col(ColKernelFn k, const ColSeg& cs, const ColGeom& g, cudaStream_t st, int threads = kColThreads, int smem_bytes = 0) {
+    if (smem_bytes > 48 * 1024) {     // opt in to large dynamic shared memory once per kernel
+        static std::mutex mu;
+        static std::map<const void*, int> done;
+        std::lock_guard<std::mutex> lk(mu);
+        if (done[(const void*)k] < smem_bytes) {
+            cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic shared memory)");
+            done[(const void*)k] = smem_bytes;
+        }
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)g.col_blocks, (unsigned)g.row_splits);
-    cfg.blockDim = dim3(kColThreads);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -231,6 +242,25 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
         if (cg.ok) {
             if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
                 return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
+            const long long upr16 = C * inner * elem_size(xdt) / 16;
+            if (tuning().col_tma > 0 && upr16 >= kTmaConsumers) {
+                // TMA-staged variant: a CTA owns 256 column units (4 KB of every row) and a contiguous run of rows
+                int smem = 0;
+                ColKernelFn tk = get_col_bwd_tma_kernel(xdt, mode, bmode_of(q), tuning().col_tma, &smem);
+                ColGeom tg = cg;
+                tg.units_per_row = upr16; tg.tx = kTmaConsumers; tg.ty = 1;
+                tg.col_blocks = (upr16 + kTmaConsumers - 1) / kTmaConsumers;
+                const int occ = smem <= 110 * 1024 ? 2 : 1;
+                long long splits = ((long long)tuning().col_waves_bwd * tuning().sm_count * occ) / tg.col_blocks;
+                if (splits < 1) splits = 1;
+                long long rows = (outer + splits - 1) / splits;
+                if (rows < 2) rows = 2;
+                tg.rows_per_split = rows;
+                tg.row_splits = (outer + rows - 1) / rows;
+                if (tg.row_splits > 65535) { tg.rows_per_split = (outer + 65534) / 65535; tg.row_splits = (outer + tg.rows_per_split - 1) / tg.rows_per_split; }
+                const ColSeg cs = make_colseg(tg, x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, pdt, q, workspace);
+                return launch_col(tk, cs, tg, st, kTmaThreads, smem);
+            }
             const ColSeg cs = make_colseg(cg, x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, pdt, q, workspace);
             return launch_col(ck, cs, cg, st);
         }
@@ -436,6 +466,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "col_variant") g_tuning.col_variant = (v >= 0 && v < kColVariants) ? v : 0;
         else if (k == "col_waves") g_tuning.col_waves = v > 0 ? v : 2;
         else if (k == "col_waves_bwd") g_tuning.col_waves_bwd = v > 0 ? v : 1;
+        else if (k == "col_tma") g_tuning.col_tma = (v >= 0 && v <= 3) ? v : 0;
         else if (k == "column_max_row_bytes") g_tuning.column_max_row_bytes = v;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;

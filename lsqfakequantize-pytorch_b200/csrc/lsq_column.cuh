@@ -255,9 +255,196 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-staged column backward (north_star: "TMA staging only where the per-channel layout makes tiles pay
+// off").  Same thread <-> column-unit mapping and arithmetic as lsq_col_bwd_kernel, but the R x 4 KB tile of
+// x and of grad (R rows of this CTA's 256 column units) is brought into shared memory by the bulk-copy
+// engine (cp.async.bulk, one 1-D copy per row and operand, no tensor map needed because every row piece is
+// contiguous), S stages deep, by a dedicated producer warp; the 8 consumer warps read their 16-byte units
+// from shared memory.  No registers hold loads in flight, so bytes in flight per SM are set by the ring
+// (S*R*8 KB per CTA) instead of by occupancy x unroll.  grad_x leaves through ordinary coalesced 128-bit stores.
+// Measured against the register-staged kernel in profiles/ (see DESIGN.md section 4).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmaConsumers = 256;                 // one 16-byte column unit each
+constexpr int kTmaThreads = kTmaConsumers + 32;    // + the producer warp
+constexpr int kTmaRowBytes = kTmaConsumers * 16;   // 4 KB of every row per CTA
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ Raw<4> lds_unit(uint32_t addr) {
+    Raw<4> r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(addr));
+    return r;
+}
+
+template <typename T, int MODE, int BMODE, int R, int S, int ST>
+__global__ void __launch_bounds__(kTmaThreads, 2)
+lsq_col_bwd_tma_kernel(const __grid_constant__ ColSeg cs) {
+    constexpr int NW = 4, VEC = ColVec<T, 4>::VEC, UB = 16;
+    constexpr int FLUSH_ROWS = 32;
+    constexpr uint32_t STAGE_BYTES = 2u * R * kTmaRowBytes;          // x rows then grad rows
+    extern __shared__ __align__(128) unsigned char ring[];           // [S][2][R][4 KB]
+    __shared__ __align__(8) unsigned long long bars[2 * S];          // full[S], empty[S]
+    __shared__ int last_flag;
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long u0 = (long long)blockIdx.x * kTmaConsumers;      // first column unit of this CTA
+    const long long left = cs.units_per_row - u0;
+    const int ncol = left < kTmaConsumers ? (int)left : kTmaConsumers;
+    const uint32_t row_bytes = (uint32_t)ncol * UB;
+    const long long n0 = (long long)blockIdx.y * cs.rows_per_split;
+    long long n_end = n0 + cs.rows_per_split;
+    if (n_end > cs.outer) n_end = cs.outer;
+    const int nrows = n_end > n0 ? (int)(n_end - n0) : 0;
+    const int niter = (nrows + R - 1) / R;
+    const uint32_t ring0 = smem_u32(ring), full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, kTmaConsumers / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long row_pitch = cs.units_per_row * UB;               // bytes between rows
+    if (warp == kTmaConsumers / 32) {
+        // ---- producer warp: one lane feeds the ring
+        if (lane == 0) {
+            const char* src_x = reinterpret_cast<const char*>(cs.x) + (n0 * cs.units_per_row + u0) * UB;
+            const char* src_g = reinterpret_cast<const char*>(cs.g) + (n0 * cs.units_per_row + u0) * UB;
+            for (int it = 0; it < niter; it++) {
+                const int s = it % S;
+                const uint32_t k = (uint32_t)(it / S);
+                mbar_wait(empty0 + 8 * s, (k & 1u) ^ 1u);             // first pass over the ring falls through
+                const int rows = nrows - it * R < R ? nrows - it * R : R;
+                mbar_expect_tx(full0 + 8 * s, 2u * (uint32_t)rows * row_bytes);
+                const uint32_t dst = ring0 + (uint32_t)s * STAGE_BYTES;
+                for (int r = 0; r < rows; r++) {
+                    tma_load_1d(dst + (uint32_t)r * kTmaRowBytes, src_x, row_bytes, full0 + 8 * s);
+                    tma_load_1d(dst + (uint32_t)(R + r) * kTmaRowBytes, src_g, row_bytes, full0 + 8 * s);
+                    src_x += row_pitch; src_g += row_pitch;
+                }
+            }
+        }
+    } else {
+        // ---- consumer warps: thread t owns column unit u0 + t
+        const int t = threadIdx.x;
+        const bool active = t < ncol;
+        const long long uc = u0 + t;
+        SlotParams<T, MODE, 4> sp;
+        float accS[VEC], accB[VEC];
+        double sumS[VEC], sumB[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; k++) { accS[k] = 0.f; accB[k] = 0.f; sumS[k] = 0.0; sumB[k] = 0.0; }
+        if (active) sp.load(cs, uc);
+        char* pgx = cs.gx ? reinterpret_cast<char*>(cs.gx) + (n0 * cs.units_per_row + uc) * UB : nullptr;
+        auto row = [&](uint32_t ax, uint32_t ag) {
+            const Raw<NW> xr = lds_unit(ax), gr = lds_unit(ag);
+            float fx[VEC], fg[VEC];
+            unpack_unit<T, NW>(xr, fx);
+            unpack_unit<T, NW>(gr, fg);
+#pragma unroll
+            for (int k = 0; k < VEC; k++)
+                fg[k] = fq_backward<MODE, BMODE, false>(fg[k], fx[k], sp.chan(k, cs), accS[k], accB[k]);
+            if (pgx) {
+                if (bmode_passthrough(BMODE)) st_unit<ST, NW>(pgx, gr);
+                else st_unit<ST, NW>(pgx, pack_unit<T, NW>(fg));
+                pgx += row_pitch;
+            }
+        };
+        int since = 0;
+        for (int it = 0; it < niter; it++) {
+            const int s = it % S;
+            const uint32_t k = (uint32_t)(it / S);
+            mbar_wait(full0 + 8 * s, k & 1u);
+            const int rows = nrows - it * R < R ? nrows - it * R : R;
+            if (active) {
+                const uint32_t ax = ring0 + (uint32_t)s * STAGE_BYTES + (uint32_t)t * UB;
+                if (rows == R) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) row(ax + (uint32_t)r * kTmaRowBytes, ax + (uint32_t)(R + r) * kTmaRowBytes);
+                } else {
+                    for (int r = 0; r < rows; r++) row(ax + (uint32_t)r * kTmaRowBytes, ax + (uint32_t)(R + r) * kTmaRowBytes);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);               // this warp is done reading stage s
+            if (bmode_reduces(BMODE) && (since += rows) >= FLUSH_ROWS) {
+                since = 0;
+#pragma unroll
+                for (int q = 0; q < VEC; q++) { sumS[q] += (double)accS[q]; accS[q] = 0.f; sumB[q] += (double)accB[q]; accB[q] = 0.f; }
+            }
+        }
+        auto slot_channel = [&](int q) { return (int)(((unsigned)uc * VEC + (unsigned)q) / (unsigned)cs.inner); };
+        if (active) {
+            if constexpr (!bmode_reduces(BMODE)) {
+                if (blockIdx.y == 0) {
+#pragma unroll
+                    for (int q = 0; q < VEC; q++) {
+                        const int c = slot_channel(q);
+                        if (q == 0 || c != slot_channel(q > 0 ? q - 1 : 0)) {
+                            store_param(cs.gscale, c, cs.pdt, 0.0);
+                            store_param(cs.gshift, c, cs.pdt, 0.0);
+                        }
+                    }
+                }
+            } else {
+                double rs = 0.0, rb = 0.0;
+#pragma unroll
+                for (int q = 0; q < VEC; q++) {
+                    rs += sumS[q] + (double)accS[q]; rb += sumB[q] + (double)accB[q];
+                    const int c = slot_channel(q);
+                    if (q == VEC - 1 || slot_channel(q + 1 < VEC ? q + 1 : q) != c) {
+                        atomicAdd(cs.acc + 2 * (long long)c, rs);
+                        atomicAdd(cs.acc + 2 * (long long)c + 1, rb);
+                        rs = 0.0; rb = 0.0;
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (bmode_reduces(BMODE)) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned prev = atomicAdd(cs.counter, 1u);
+            last_flag = (prev == cs.total_ctas - 1u);
+        }
+        __syncthreads();
+        if (!last_flag) return;
+        __threadfence();
+        for (long long c = threadIdx.x; c < cs.C; c += kTmaThreads) {
+            const double a = __ldcg(cs.acc + 2 * c), b = __ldcg(cs.acc + 2 * c + 1);
+            store_param(cs.gscale, c, cs.pdt, a * cs.gs);
+            store_param(cs.gshift, c, cs.pdt, cs.sym ? 0.0 : b * cs.gs);
+            cs.acc[2 * c] = 0.0; cs.acc[2 * c + 1] = 0.0;
+        }
+        if (threadIdx.x == 0) *cs.counter = 0u;
+    }
+}
+
 using ColKernelFn = void (*)(const ColSeg);
 ColKernelFn get_col_fwd_kernel(int xdtype, int mode, bool init, int variant);
 ColKernelFn get_col_bwd_kernel(int xdtype, int mode, int bmode, int variant);
+// TMA-staged backward: tma_variant 1 = (R 4 rows, S 3 stages, 96 KB ring), 2 = (2, 4, 64 KB), 3 = (8, 3, 192 KB); sets *smem_bytes
+ColKernelFn get_col_bwd_tma_kernel(int xdtype, int mode, int bmode, int tma_variant, int* smem_bytes);
 // variant -> (unit words, rows in flight, min CTAs/SM); index with Tuning::col_variant
 constexpr int kColVariants = 6;
 constexpr int kColVariantNW[kColVariants] = {4, 4, 2, 2, 4, 4};

@@ -84,6 +84,7 @@ struct Tuning {
     int column_path = 1;        // short channel rows (channels-last, 7x7 / 14x14 maps) use the column-layout kernels
     int col_variant = 1;        // column kernels: 0 = 128-bit units x2 rows, 1 = x4 rows (default, r1 sweep), 2 = 64-bit units x4 rows, 3 = x8 rows
     int col_waves = 2;          // column forward: CTAs <= col_waves * sm_count * (resident CTAs/SM of the kernel), rounded DOWN to whole waves
+    int col_tma = 0;            // column backward staged by the bulk-copy engine (lsq_col_bwd_tma_kernel): 0 off, 1 = 4 rows x 3 stages, 2 = 2 x 4, 3 = 8 x 3
     int col_waves_bwd = 1;      // column backward: one wave (per-thread set-up and the per-CTA atomics are paid once per row split; s6 sweep)
     int column_max_row_bytes = 512;   // rows shorter than this (or not 16 B multiples) take the column path
     int whole_waves = 1;        // round big-tensor tile counts to whole waves of resident CTAs
