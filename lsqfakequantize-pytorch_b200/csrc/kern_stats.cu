@@ -4,7 +4,7 @@ namespace lsqb200 {
 namespace {
 template <typename T, int NW>
 KernelFn pick_g(int group) {
-#define LSQ_S(G_) lsq_stats_kernel<T, NW, G_, kThreads, unroll_for(kUnrollStats, NW, G_), kLd, kMinBlocksStats>
+#define LSQ_S(G_) lsq_stats_kernel<T, NW, G_, kThreads, unroll_for_stats(kUnrollStats, NW, G_), kLd, kMinBlocksStats>
     return group == 32 ? LSQ_S(32) : LSQ_S(kThreads);
 #undef LSQ_S
 }

@@ -21,11 +21,25 @@ constexpr int kUnrollBwd = 2;
 constexpr int kUnrollStats = 4;
 // units in flight per thread and operand: keep ~64 bytes per operand whatever the unit width
 // warp groups own short rows and have little else to overlap their latency with: twice the units in flight
+// Warp groups (one warp per short channel row, e.g. every ResNet-50 weight row): same units in flight and the same
+// resident CTAs as the CTA groups.  Session-7 A/B on the 54-weight plan (tools/ab_variants.sh): 1 unit in flight x 4 / 6
+// CTAs per SM 4835 GB/s, 2 units x 3 CTAs 4655, 2 units x 2 CTAs (the earlier default, 116 registers) 4186 - the rows'
+// set-up and reduce phases overlap better with more warps than with deeper per-warp prefetch.
+#ifndef LSQ_WG_UMUL
+#define LSQ_WG_UMUL 1          // warp groups: units in flight relative to CTA groups (experiment knob)
+#endif
+#ifndef LSQ_WG_MINB_NUM
+#define LSQ_WG_MINB_NUM 1      // warp groups: min CTAs/SM = base * NUM / DEN
+#define LSQ_WG_MINB_DEN 1
+#endif
 constexpr int unroll_for(int base, int nw, int group = 256) {
-    return (nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base) * (group == 32 ? 2 : 1);
+    return (nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base) * (group == 32 ? LSQ_WG_UMUL : 1);
 }
+// the read-only statistics kernel keeps two units in flight per lane for warp groups (2490 vs 2264 GB/s on the 54 weights)
+constexpr int unroll_for_stats(int base, int nw, int group) { return (nw == 8 ? (base / 2 > 0 ? base / 2 : 1) : base) * (group == 32 ? 2 : 1); }
 constexpr int kMinBlocksStats = 2;
-constexpr int minb_for(int base, int group) { return group == 32 ? (base * 2 / 3 > 0 ? base * 2 / 3 : 1) : base; }
+constexpr int kResidentStats = 4;   // CTAs/SM the statistics / observer kernels really get (<= 64 registers): whole-wave rounding uses this
+constexpr int minb_for(int base, int group) { return group == 32 ? (base * LSQ_WG_MINB_NUM / LSQ_WG_MINB_DEN > 0 ? base * LSQ_WG_MINB_NUM / LSQ_WG_MINB_DEN : 1) : base; }
 constexpr int kMinBlocksFwd = 6;   // __launch_bounds__ min CTAs/SM -> register cap 40
 constexpr int kMinBlocksBwd = 4;   // -> register cap 64
 constexpr int kLd = LD_NC_NOALLOC;   // streaming loads: read-only path, no L1 allocation
@@ -143,7 +157,7 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
     // whole waves: when a channel is cut into more tiles than fit on the machine at once, round
     // the count up to a multiple of the resident CTA slots so the last wave is full
     if (C == 1) {
-        const long long resident = (long long)tn.sm_count * (kind == K_BWD ? kMinBlocksBwd : (kind == K_FWD ? kMinBlocksFwd : kMinBlocksStats));
+        const long long resident = (long long)tn.sm_count * (kind == K_BWD ? kMinBlocksBwd : (kind == K_FWD ? kMinBlocksFwd : kResidentStats));
         if (tn.whole_waves && splits > resident) {
             const long long r = (splits + resident - 1) / resident * resident;
             if (r <= max_splits) splits = r;

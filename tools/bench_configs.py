@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Per-config measurements for BASELINE.json configs[0..3] on one B200 (bench.py covers configs[4]).
 
-CUDA-event timing, median of `--iters` after warm-up; working sets under 256 MB get a 512 MB
-L2-flush write between iterations (outside the timed events).  GB/s = algorithmic bytes / time
+CUDA-event timing, median of `--iters` after warm-up; a 512 MB L2-flush write is enqueued in front of the
+timed events of every iteration (outside them): it empties L2 for the small working sets and keeps the GPU
+busy while the host prepares the call, so wrapper latency is not counted as kernel time.  GB/s = algorithmic bytes / time
 (5*sizeof(T) per element for fwd+bwd, 1*sizeof(T) for the mu+-3sigma statistics).
 Prints one JSON object; copy it to profiles/ to keep it.
 """
@@ -26,12 +27,15 @@ from torchlsq.multi import LSQPlan, Site  # noqa: E402
 DEV = "cuda:0"
 
 
-def timed(fn, iters, flush):
+def timed(fn, iters, flush, cover=1):
+    """`cover` flush writes (about 80 us of GPU time each) are queued in front of the timed events so the host side of
+    `fn` (Python wrappers take up to ~100 us) runs while the GPU is still busy and is not counted as kernel time."""
     times = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for i in range(iters + 3):
         if flush is not None:
-            flush.fill_(i)
+            for _ in range(cover):
+                flush.fill_(i)
         e0.record()
         fn()
         e1.record()
@@ -149,7 +153,7 @@ def main():
         lib.lsqb200_fwd_channel(x4.data_ptr(), y4.data_ptr(), s4.data_ptr(), b4.data_ptr(), N, C, HW, 1, 0, q, sp)
         lib.lsqb200_bwd_channel(g4.data_ptr(), x4.data_ptr(), gx4.data_ptr(), s4.data_ptr(), b4.data_ptr(), gs4.data_ptr(), gb4.data_ptr(),
                                 N, C, HW, 1, 0, q, ws.data_ptr(), ws.numel(), sp)
-    report("config4_per_channel_fp16_256x1024x28x28_fwd_bwd", 5 * 2 * x4.numel(), *timed(c4, args.iters, None), l2="1.6 GB working set", launches=2)
+    report("config4_per_channel_fp16_256x1024x28x28_fwd_bwd", 5 * 2 * x4.numel(), *timed(c4, args.iters, flush), l2="1.6 GB working set", launches=2)
     # same tensor, other per-channel layouts the ResNet activations produce
     for hw, cc in ((196, 1024), (49, 2048), (3136, 256)):
         nn_ = N * cc * hw
@@ -160,7 +164,7 @@ def main():
             lib.lsqb200_fwd_channel(x4.data_ptr(), y4.data_ptr(), sc.data_ptr(), bc.data_ptr(), N, cc, hw, 1, 0, q, sp)
             lib.lsqb200_bwd_channel(g4.data_ptr(), x4.data_ptr(), gx4.data_ptr(), sc.data_ptr(), bc.data_ptr(), gsc.data_ptr(), gbc.data_ptr(),
                                     N, cc, hw, 1, 0, q, ws.data_ptr(), ws.numel(), sp)
-        report(f"per_channel_fp16_256x{cc}x{hw}_fwd_bwd", 5 * 2 * nn_, *timed(cx, max(5, args.iters // 2), None), l2="large", launches=2)
+        report(f"per_channel_fp16_256x{cc}x{hw}_fwd_bwd", 5 * 2 * nn_, *timed(cx, max(5, args.iters // 2), flush), l2="large", launches=2)
     # channels-last per-channel (inner = 1)
     nn_ = 256 * 196 * 1024
     sc, bc = 0.02 + 0.02 * torch.rand(1024, device=DEV), -torch.rand(1024, device=DEV)
@@ -170,7 +174,7 @@ def main():
         lib.lsqb200_fwd_channel(x4.data_ptr(), y4.data_ptr(), sc.data_ptr(), bc.data_ptr(), 256 * 196, 1024, 1, 1, 0, q, sp)
         lib.lsqb200_bwd_channel(g4.data_ptr(), x4.data_ptr(), gx4.data_ptr(), sc.data_ptr(), bc.data_ptr(), gsc.data_ptr(), gbc.data_ptr(),
                                 256 * 196, 1024, 1, 1, 0, q, ws.data_ptr(), ws.numel(), sp)
-    report("per_channel_fp16_channels_last_50176x1024_fwd_bwd", 5 * 2 * nn_, *timed(cl, 5, None), l2="large", launches=2)
+    report("per_channel_fp16_channels_last_50176x1024_fwd_bwd", 5 * 2 * nn_, *timed(cl, 5, flush), l2="large", launches=2)
     # ---- observer-mode init step: fused native step vs torch's observer + host logic, 256x256x56x56 bf16
     import warnings
     from torchlsq.quantized.modules.observers import observer_step
@@ -185,23 +189,23 @@ def main():
         obs_t(xo)
         sc, zp = obs_t.calculate_qparams()
         so.copy_(sc); bo.copy_(-zp * so)
-    report("observer_step_native_bf16_411MB", 2 * xo.numel(), *timed(lambda: observer_step(obs_n, xo, so, bo), args.iters, None), l2="411 MB", launches=1)
-    report("observer_step_torch_path_bf16_411MB", 2 * xo.numel(), *timed(torch_path, max(5, args.iters // 2), None), l2="411 MB",
+    report("observer_step_native_bf16_411MB", 2 * xo.numel(), *timed(lambda: observer_step(obs_n, xo, so, bo), args.iters, flush, cover=3), l2="411 MB", launches=1)
+    report("observer_step_torch_path_bf16_411MB", 2 * xo.numel(), *timed(torch_path, max(5, args.iters // 2), flush), l2="411 MB",
            note="x.to(float32) + aminmax + qparams kernels + host syncs, as the reference module does")
     # ---- integer export: bf16 activation -> uint8 codes (3 B / element), codes -> bf16, vs torch's own path
     from torchlsq import export as EX
     s1, b1 = torch.tensor([0.03], device=DEV), torch.tensor([-1.7], device=DEV)
     xe = xo.view(256, 256, 56, 56)
     for sem in ("lsq", "torch"):
-        report(f"export_quantize_{sem}_bf16_to_u8_411MB", 3 * xe.numel(), *timed(lambda: EX.quantize(xe, s1, b1, 0, 127, 0, 255, semantics=sem), args.iters, None),
+        report(f"export_quantize_{sem}_bf16_to_u8_411MB", 3 * xe.numel(), *timed(lambda: EX.quantize(xe, s1, b1, 0, 127, 0, 255, semantics=sem), args.iters, flush, cover=3),
                l2="411 MB in", launches=1)
     ce = EX.quantize(xe, s1, b1, 0, 127, 0, 255)
-    report("export_dequantize_lsq_u8_to_bf16_205MB", 3 * xe.numel(), *timed(lambda: EX.dequantize(ce, s1, b1, 0, 127, 0, 255, dtype=torch.bfloat16), args.iters, None),
+    report("export_dequantize_lsq_u8_to_bf16_205MB", 3 * xe.numel(), *timed(lambda: EX.dequantize(ce, s1, b1, 0, 127, 0, 255, dtype=torch.bfloat16), args.iters, flush, cover=3),
            l2="205 MB in", launches=1)
     xf = xe[:64].float()
-    report("export_torch_quantize_per_tensor_f32_205MB", 5 * xf.numel(), *timed(lambda: torch.quantize_per_tensor(xf, 0.03, 57, torch.quint8), max(5, args.iters // 2), None),
+    report("export_torch_quantize_per_tensor_f32_205MB", 5 * xf.numel(), *timed(lambda: torch.quantize_per_tensor(xf, 0.03, 57, torch.quint8), max(5, args.iters // 2), flush),
            l2="205 MB in", note="torch's CUDA quantizer (fp32 input only), for comparison")
-    report("export_quantize_torch_f32_to_u8_205MB", 5 * xf.numel(), *timed(lambda: EX.quantize(xf, s1, b1, 0, 127, 0, 255, semantics='torch'), args.iters, None),
+    report("export_quantize_torch_f32_to_u8_205MB", 5 * xf.numel(), *timed(lambda: EX.quantize(xf, s1, b1, 0, 127, 0, 255, semantics='torch'), args.iters, flush, cover=3),
            l2="205 MB in", launches=1)
     print(json.dumps(out, indent=1))
 
