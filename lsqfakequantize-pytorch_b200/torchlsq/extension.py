@@ -58,6 +58,15 @@ def _dense_layout(x: torch.Tensor, axis=None):
     """
     if x.numel() == 0:
         return x, 0, (x.shape[axis] if axis is not None else 1), 0
+    if x.is_contiguous():                        # the common case, no Python loops over strides
+        if axis is None:
+            return x, 1, 1, x.numel()
+        shape = x.shape
+        outer = 1
+        for d in range(axis):
+            outer *= shape[d]
+        C = shape[axis]
+        return x, outer, C, x.numel() // (outer * C)
     dims = [d for d in range(x.dim()) if x.shape[d] != 1 or d == axis]
     order = sorted(dims, key=lambda d: (-x.stride(d), d))
     expect, dense = 1, True
@@ -108,8 +117,47 @@ def _match_layout(grad, xd):
     return out
 
 
+try:
+    _raw_stream = torch._C._cuda_getCurrentRawStream          # (device_index) -> cudaStream_t as int, ~0.3 us
+except AttributeError:                                        # pragma: no cover
+    _raw_stream = None
+
+
 def _stream_ptr(device):
+    if _raw_stream is not None and device.index is not None:
+        return _raw_stream(device.index)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _NoCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def _on_device(device):
+    """`with torch.cuda.device(d)` costs ~10 us; it is only needed when d is not the current device."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NOCTX
+    return torch.cuda.device(device)
+
+
+_qargs_cache = {}
+
+
+def _qargs(*scalars):
+    """lsqb200_qargs structs are immutable inputs: one per distinct scalar tuple."""
+    q = _qargs_cache.get(scalars)
+    if q is None:
+        if len(_qargs_cache) > 4096:
+            _qargs_cache.clear()
+        q = _qargs_cache[scalars] = _cabi.qargs(*scalars)
+    return q
 
 
 def _fwd_tensor_cuda(x, scale, shift, quant_min, quant_max, type_min, type_max,
@@ -122,8 +170,8 @@ def _fwd_tensor_cuda(x, scale, shift, quant_min, quant_max, type_min, type_max,
     y = torch.empty_like(xd)
     if n == 0:
         return y
-    q = _cabi.qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
-    with torch.cuda.device(x.device):
+    q = _qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
+    with _on_device(x.device):
         rc = lib.lsqb200_fwd_tensor(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), n,
                                     _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
     _cabi.check(rc, "lsq_forward_per_tensor")
@@ -143,8 +191,8 @@ def _bwd_tensor_cuda(grad, x, scale, shift, quant_min, quant_max, type_min, type
     gx = torch.empty_like(xd)
     gscale = torch.empty(1, dtype=scale.dtype, device=scale.device)
     gshift = torch.empty(1, dtype=shift.dtype, device=shift.device)
-    q = _cabi.qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
-    with torch.cuda.device(x.device):
+    q = _qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
+    with _on_device(x.device):
         sp = _stream_ptr(x.device)
         ws = _workspace(x.device, sp)
         rc = lib.lsqb200_bwd_tensor(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
@@ -176,8 +224,8 @@ def _fwd_channel_cuda(x, scale, shift, axis, quant_min, quant_max, type_min, typ
     y = torch.empty_like(xd)
     if x.numel() == 0:
         return y
-    q = _cabi.qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
-    with torch.cuda.device(x.device):
+    q = _qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
+    with _on_device(x.device):
         rc = lib.lsqb200_fwd_channel(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
                                      _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
     _cabi.check(rc, "lsq_forward_per_channel")
@@ -198,8 +246,8 @@ def _bwd_channel_cuda(grad, x, scale, shift, axis, quant_min, quant_max, type_mi
     gx = torch.empty_like(xd)
     gscale = torch.empty(C, dtype=scale.dtype, device=scale.device)
     gshift = torch.empty(C, dtype=shift.dtype, device=shift.device)
-    q = _cabi.qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
-    with torch.cuda.device(x.device):
+    q = _qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
+    with _on_device(x.device):
         sp = _stream_ptr(x.device)
         ws = _workspace(x.device, sp)
         rc = lib.lsqb200_bwd_channel(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
@@ -264,8 +312,11 @@ class _LSQPerTensorFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, scale, shift, *scalars):
-        with torch._C._AutoDispatchBelowAutograd():
-            out = torch.ops.torchlsq.lsq_forward_per_tensor(x, scale, shift, *scalars)
+        if x.is_cuda:                                  # straight to the kernel launcher: no second dispatcher hop
+            out = _fwd_tensor_cuda(x, scale, shift, *scalars)
+        else:
+            with torch._C._AutoDispatchBelowAutograd():
+                out = torch.ops.torchlsq.lsq_forward_per_tensor(x, scale, shift, *scalars)
         ctx.scalars = scalars
         ctx.save_for_backward(x, scale, shift)
         return out
@@ -273,7 +324,10 @@ class _LSQPerTensorFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         x, scale, shift = ctx.saved_tensors
-        gx, gs, gb = torch.ops.torchlsq.lsq_backward_per_tensor(grad_output, x, scale, shift, *ctx.scalars)
+        if x.is_cuda and not torch.is_grad_enabled():
+            gx, gs, gb = _bwd_tensor_cuda(grad_output, x, scale, shift, *ctx.scalars)
+        else:   # create_graph=True: through the dispatcher, whose Autograd entry refuses the double backward
+            gx, gs, gb = torch.ops.torchlsq.lsq_backward_per_tensor(grad_output, x, scale, shift, *ctx.scalars)
         return (gx, gs, gb) + (None,) * 9
 
 
@@ -282,8 +336,11 @@ class _LSQPerChannelFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, scale, shift, axis, *scalars):
-        with torch._C._AutoDispatchBelowAutograd():
-            out = torch.ops.torchlsq.lsq_forward_per_channel(x, scale, shift, axis, *scalars)
+        if x.is_cuda:
+            out = _fwd_channel_cuda(x, scale, shift, axis, *scalars)
+        else:
+            with torch._C._AutoDispatchBelowAutograd():
+                out = torch.ops.torchlsq.lsq_forward_per_channel(x, scale, shift, axis, *scalars)
         ctx.axis = axis
         ctx.scalars = scalars
         ctx.save_for_backward(x, scale, shift)
@@ -292,7 +349,10 @@ class _LSQPerChannelFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         x, scale, shift = ctx.saved_tensors
-        gx, gs, gb = torch.ops.torchlsq.lsq_backward_per_channel(grad_output, x, scale, shift, ctx.axis, *ctx.scalars)
+        if x.is_cuda and not torch.is_grad_enabled():
+            gx, gs, gb = _bwd_channel_cuda(grad_output, x, scale, shift, ctx.axis, *ctx.scalars)
+        else:
+            gx, gs, gb = torch.ops.torchlsq.lsq_backward_per_channel(grad_output, x, scale, shift, ctx.axis, *ctx.scalars)
         return (gx, gs, gb) + (None,) * 10
 
 
@@ -307,9 +367,15 @@ def _lsq_front(x, scale, shift, quant_min, quant_max, type_min, type_max, axis, 
         size = max(scale.size(0), shift.size(0))
         _scale = scale if size == scale.size(0) else scale.repeat(size)
         _shift = shift if size == shift.size(0) else shift.repeat(size)
+        if x.is_cuda:     # same autograd node the dispatcher's Autograd entry would build, minus two Python dispatcher hops
+            return _LSQPerChannelFunction.apply(x, _scale, _shift, axis, quant_min, quant_max, type_min, type_max,
+                                                use_grad_scaling, grad_scaler, not is_affine, eval_mode, init_mode)
         return torch.ops.torchlsq.lsq_forward_per_channel(x, _scale, _shift, axis, quant_min, quant_max, type_min,
                                                           type_max, use_grad_scaling, grad_scaler, not is_affine,
                                                           eval_mode, init_mode)
+    if x.is_cuda:
+        return _LSQPerTensorFunction.apply(x, scale, shift, quant_min, quant_max, type_min, type_max,
+                                           use_grad_scaling, grad_scaler, not is_affine, eval_mode, init_mode)
     return torch.ops.torchlsq.lsq_forward_per_tensor(x, scale, shift, quant_min, quant_max, type_min, type_max,
                                                      use_grad_scaling, grad_scaler, not is_affine, eval_mode, init_mode)
 
