@@ -64,35 +64,47 @@ assert len(W_SHAPES) == 54 and sum(math.prod(s) for s in W_SHAPES) == 25_502_912
 # -------------------------------------------------------------------------------------------------
 class ClockSampler:
     def __init__(self, index):
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.reasons, self.max_mhz, self.error = index, [], set(), None, None
         self._stop = threading.Event()
         self._t = None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.h = None
+            try:    # NVML enumerates every GPU of the box; CUDA may see a subset / another order: go by PCI address
+                import torch
+                pr = torch.cuda.get_device_properties(index)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = None
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception:
             self.nv = None
 
-    def _run(self):
+    def _sample(self):
         nv = self.nv
         names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
                  "hw_power_brake": 0x80}
-        while not self._stop.is_set():
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            self._stop.wait(0.05)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in names.items():
+                if r & bit:
+                    self.reasons.add(k)
+        except Exception as exc:
+            self.error = repr(exc)
+
+    def _run(self):
+        while not self._stop.is_set():
+            self._sample()
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv:
@@ -101,13 +113,15 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.nv:
+            self._sample()        # the GPU has just finished the timed region: a short run still gets a sample under load
         self._stop.set()
         if self._t:
             self._t.join()
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled" + (": " + self.error if self.error else "")]}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
@@ -318,6 +332,25 @@ def run_b200(args):
     barrier()
     # sanity: the C ABI must have really run (outputs finite, grads written)
     assert torch.isfinite(flat.flat).all().item() and flat.flat.abs().sum().item() > 0
+    dp_check = None
+    if world > 1:
+        # data-parallel semantics on the real NCCL path: all-reduced buffer == sum over ranks of the local grads
+        # (each rank scaled with its LOCAL numel), checked on every rank
+        from torchlsq.dp import expected_allreduced
+        for c in fwd_calls:
+            fwd_t(*c)
+        wplan.forward()
+        for c in bwd_calls:
+            bwd_t(*c)
+        wplan.backward()
+        local = flat.flat.clone()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        flat.all_reduce()
+        want = expected_allreduced(gathered)
+        err = ((flat.flat.double() - want).abs() / (want.abs() + 1e-12)).max().item()
+        assert err < 1e-6, f"all-reduced scale/shift grads differ from the sum of the shards' grads: {err}"
+        dp_check = {"max_rel_err_vs_sum_of_shard_grads": err, "floats": flat.numel}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     bw = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
@@ -428,7 +461,7 @@ def run_b200(args):
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": bwd_bytes, "avg_ms_per_step": round(bwd_ms, 4)},
-            "plan_mode": plan_mode, "weight_init_stats_GBps": round(init_gbps, 1),
+            "plan_mode": plan_mode, "weight_init_stats_GBps": round(init_gbps, 1), "dp_check": dp_check,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(),
         }
