@@ -154,6 +154,24 @@ LSQB200_API int lsqb200_dequantize(const void* codes, void* y, const void* scale
 LSQB200_API int lsqb200_qparams(const void* scale, const void* shift, float* scale_out, int64_t* zero_point_out,
                     int64_t n, int pdtype, int64_t type_min, int64_t type_max, void* stream);
 
+/* ---- fused parameter step: ONE launch updates every LSQ scale / shift parameter of a model from
+ *      the flat gradient buffer the backward kernels (and the data-parallel all-reduce) filled - torch.optim's SGD / Adam
+ *      arithmetic (single-tensor path, fp32), with DDP's 1/world averaging folded in as grad_mul.  The reference leaves the
+ *      update of its lazily created parameters to the user's optimizer (README.md:101). ------------------------------------ */
+#define LSQB200_OPT_SGD 0
+#define LSQB200_OPT_ADAM 1
+typedef struct lsqb200_optim_args {
+    double lr, weight_decay, grad_mul;        /* grad_mul: e.g. 1 / world_size (1 = plain sum) */
+    double momentum, dampening;               /* SGD */
+    double beta1, beta2, eps;                 /* Adam */
+    int64_t step;                             /* 1-based count of this update (Adam bias correction, SGD momentum-buffer init) */
+    int32_t kind;                             /* LSQB200_OPT_SGD / LSQB200_OPT_ADAM */
+    int32_t nesterov;
+} lsqb200_optim_args;
+/* params / grads: float[n]; state1: momentum buffer (SGD with momentum) or exp_avg (Adam); state2: exp_avg_sq (Adam) or NULL. */
+LSQB200_API int lsqb200_flat_optimizer_step(float* params, const float* grads, float* state1, float* state2, int64_t n,
+                                const lsqb200_optim_args* args, void* stream);
+
 /* ---- multi-tensor plans: one launch for many fake-quant sites (the 54 ResNet-50 weights, or
  *      every site of a step).  Semantics per segment are exactly those of the calls above. --- */
 typedef struct lsqb200_segment {

@@ -37,6 +37,16 @@ class ObserverArgs(Structure):
                 ("moving_average", c_int32), ("symmetric", c_int32), ("zero_point_sym", c_int32), ("reserved", c_int32)]
 
 
+class OptimArgs(Structure):
+    """lsqb200_optim_args -- torch.optim SGD / Adam hyper-parameters of one fused flat-buffer step."""
+    _fields_ = [("lr", c_double), ("weight_decay", c_double), ("grad_mul", c_double), ("momentum", c_double),
+                ("dampening", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double),
+                ("step", c_int64), ("kind", c_int32), ("nesterov", c_int32)]
+
+
+OPT_SGD, OPT_ADAM = 0, 1
+
+
 class LaunchInfo(Structure):
     _fields_ = [("regime", c_int32), ("vec", c_int32), ("threads", c_int32), ("splits", c_int32),
                 ("grid", c_int64), ("units_per_split", c_int64)]
@@ -65,6 +75,7 @@ _PROTOTYPES = {
     "lsqb200_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_int,
                                    POINTER(QArgs), c_int, c_int, c_void_p]),
     "lsqb200_qparams": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p]),
+    "lsqb200_flat_optimizer_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(OptimArgs), c_void_p]),
     "lsqb200_plan_create": (c_int, [POINTER(Segment), c_int32, POINTER(c_void_p)]),
     "lsqb200_plan_forward": (c_int, [c_void_p, c_void_p]),
     "lsqb200_plan_backward": (c_int, [c_void_p, c_void_p]),

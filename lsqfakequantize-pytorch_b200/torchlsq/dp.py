@@ -84,6 +84,91 @@ class FlatGradBuffer:
                 shift.grad = gb.view_as(shift)
 
 
+class FlatLSQOptimizer:
+    """One flat parameter buffer + one flat gradient buffer + ONE fused update launch for every LSQ scale / shift
+    parameter of a model.
+
+    Call it after the warm-up forward that creates the parameters (the reference's rule, README.md:101: "make a test
+    forward pass BEFORE adding model parameters to optimizer").  Every `scale` / `shift` parameter is re-pointed at a
+    slice of one flat fp32 buffer and its `.grad` at the matching slice of a `FlatGradBuffer`, so that
+
+        opt.zero_grad(); loss.backward(); opt.step()
+
+    costs one all-reduce (when torch.distributed is initialised; `average=True` folds DDP's 1/world into the update)
+    and one kernel launch, whatever the number of fake-quant sites.  The update is torch.optim.SGD's / Adam's
+    single-tensor arithmetic in fp32 (csrc/kern_optim.cu).  Parameters that do not require grad (symmetric shifts, static
+    quantizers) keep a zero gradient: with weight_decay = 0 they do not move.
+    """
+
+    def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter, Optional[torch.nn.Parameter]]], kind: str = "sgd",
+                 lr: float = 1e-3, momentum: float = 0.0, dampening: float = 0.0, nesterov: bool = False, weight_decay: float = 0.0,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8, average: bool = True, group=None):
+        from . import _cabi
+        if kind not in ("sgd", "adam"):
+            raise ValueError("kind must be 'sgd' or 'adam'")
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        named_params = list(named_params)
+        if not named_params:
+            raise ValueError("no LSQ parameters given (run one forward pass first: the modules create them lazily)")
+        dev = named_params[0][1].device
+        for name, scale, shift in named_params:
+            for t in (scale, shift):
+                if t is not None and (t.dtype != torch.float32 or t.device != dev or not t.is_cuda):
+                    raise RuntimeError(f"site {name!r}: LSQ parameters must be float32 CUDA tensors on one device")
+            if shift is not None and shift.numel() != scale.numel():
+                raise RuntimeError(f"site {name!r}: scale and shift differ in length")
+        self._cabi = _cabi
+        self.kind, self.lr, self.momentum, self.dampening, self.nesterov = kind, lr, momentum, dampening, nesterov
+        self.weight_decay, self.betas, self.eps, self.average, self.group = weight_decay, betas, eps, average, group
+        self.grads = FlatGradBuffer([(name, scale.numel()) for name, scale, _ in named_params], dev)
+        self.params = torch.zeros_like(self.grads.flat)
+        self.sites = named_params
+        for name, scale, shift in named_params:
+            off, n = self.grads.offsets[name]
+            ps, pb = self.params[off:off + n], self.params[off + n:off + 2 * n]
+            with torch.no_grad():
+                ps.copy_(scale.detach().reshape(-1))
+                scale.data = ps.view_as(scale)
+                scale.grad = self.grads.gscale(name).view_as(scale)
+                if shift is not None:
+                    pb.copy_(shift.detach().reshape(-1))
+                    shift.data = pb.view_as(shift)
+                    shift.grad = self.grads.gshift(name).view_as(shift)
+        self.state1 = torch.zeros_like(self.params) if (kind == "adam" or momentum != 0) else None
+        self.state2 = torch.zeros_like(self.params) if kind == "adam" else None
+        self.steps = 0
+
+    @classmethod
+    def from_model(cls, model: torch.nn.Module, **kw):
+        """Collect every module that owns `scale` and `shift` Parameters (LSQFakeQuantizer), named by its module path."""
+        found = []
+        for name, m in model.named_modules():
+            sc, sh = getattr(m, "scale", None), getattr(m, "shift", None)
+            if isinstance(sc, torch.nn.Parameter) and hasattr(m, "fake_quant_enabled"):
+                found.append((name or "root", sc, sh if isinstance(sh, torch.nn.Parameter) else None))
+        return cls(found, **kw)
+
+    def zero_grad(self):
+        """Zero the flat gradient buffer in place (autograd keeps accumulating into the same slices)."""
+        self.grads.zero_()
+
+    def step(self):
+        world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.grads.all_reduce(group=self.group)            # SUM; the 1/world of DDP-style averaging is folded into the update
+        self.steps += 1
+        a = self._cabi.OptimArgs(float(self.lr), float(self.weight_decay), 1.0 / world if self.average else 1.0, float(self.momentum),
+                                 float(self.dampening), float(self.betas[0]), float(self.betas[1]), float(self.eps), int(self.steps),
+                                 self._cabi.OPT_ADAM if self.kind == "adam" else self._cabi.OPT_SGD, int(self.nesterov))
+        dev = self.params.device
+        with torch.cuda.device(dev):
+            rc = self._cabi.load().lsqb200_flat_optimizer_step(
+                self.params.data_ptr(), self.grads.flat.data_ptr(), self.state1.data_ptr() if self.state1 is not None else None,
+                self.state2.data_ptr() if self.state2 is not None else None, self.params.numel(), a,
+                torch.cuda.current_stream(dev).cuda_stream)
+        self._cabi.check(rc, "lsqb200_flat_optimizer_step")
+
+
 class _Done:
     def wait(self):
         return None
