@@ -103,6 +103,41 @@ LSQB200_API int lsqb200_bwd_channel(const void* grad, const void* x, void* gx,
                         const lsqb200_qargs* q, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* ---- prologue fusion (not in the reference, where the ops in front of a fake-quant site are
+ *      separate ATen passes: add writes x + x2, relu reads it and writes relu(..) to HBM, csrc/ops/cuda/lsq_cuda.cu:18-61
+ *      reads that back, and the backward makes the same trips in reverse).  With a prologue the site's input is formed
+ *      in registers, x' = x (NONE) | max(x, 0) (RELU) | max(x + x2, 0) (ADD_RELU: the residual join of a ResNet block)
+ *      | x + x2 (ADD), where the sum is rounded to the tensor type exactly as ATen's add stores it and max is torch.relu
+ *      (NaN stays NaN, -0 -> +0):
+ *        forward   y  = lsq_forward(x')
+ *        backward  gx = (relu and x' <= 0) ? 0 : lsq_grad_x(grad, x');  grad_scale / grad_shift as the plain call on x'
+ *      i.e. bit for bit what the separate passes + autograd return (gx is the gradient of x and, for the ADD
+ *      prologues, of x2 as well), in 2 / 3 tensor trips (RELU: instead of 4 / 6) or 3 / 4 (ADD_RELU: instead of 7 / 6).
+ *      With init_mode (learned init) y = x' and gx = relu-masked grad.
+ *      x2: second addend, same dtype and (outer, C, inner) layout as x; ignored (may be NULL) unless the prologue adds.
+ *      Supported for float32 / float16 / bfloat16 tensors with float32 (or, for bfloat16, bfloat16) scale / shift;
+ *      other pairs return LSQB200_ERR_DTYPE.  All other arguments as in the calls above. ---------------------------- */
+#define LSQB200_PRE_NONE 0
+#define LSQB200_PRE_RELU 1
+#define LSQB200_PRE_ADD_RELU 2
+#define LSQB200_PRE_ADD 3
+LSQB200_API int lsqb200_fwd_tensor_pre(const void* x, const void* x2, void* y, const void* scale, const void* shift,
+                           int64_t numel, int xdtype, int pdtype,
+                           const lsqb200_qargs* q, int prologue, void* stream);
+LSQB200_API int lsqb200_bwd_tensor_pre(const void* grad, const void* x, const void* x2, void* gx,
+                           const void* scale, const void* shift, void* gscale, void* gshift,
+                           int64_t numel, int xdtype, int pdtype,
+                           const lsqb200_qargs* q, int prologue, void* workspace, size_t workspace_bytes,
+                           void* stream);
+LSQB200_API int lsqb200_fwd_channel_pre(const void* x, const void* x2, void* y, const void* scale, const void* shift,
+                            int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype,
+                            const lsqb200_qargs* q, int prologue, void* stream);
+LSQB200_API int lsqb200_bwd_channel_pre(const void* grad, const void* x, const void* x2, void* gx,
+                            const void* scale, const void* shift, void* gscale, void* gshift,
+                            int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype,
+                            const lsqb200_qargs* q, int prologue, void* workspace, size_t workspace_bytes,
+                            void* stream);
+
 /* ---- mu +- 3 sigma weight initialisation: replaces the torch.mean / torch.std passes of
  *      LSQFakeQuantizer._init_weights, quantized/modules/observers.py:329-337.
  *      scale_out: float[C]; C == 1 gives the whole-tensor statistic. ------------------------- */
@@ -186,8 +221,9 @@ typedef struct lsqb200_segment {
     int64_t outer, C, inner; /* per-tensor: outer = 1, C = 1, inner = numel */
     int32_t xdtype, pdtype;
     int32_t per_channel;
-    int32_t reserved;
+    int32_t prologue;   /* LSQB200_PRE_*: see lsqb200_fwd_tensor_pre (0 = none) */
     lsqb200_qargs q;
+    const void* x2;     /* second addend of the ADD prologues (same layout as x), else NULL */
 } lsqb200_segment;
 
 typedef struct lsqb200_plan lsqb200_plan; /* opaque */

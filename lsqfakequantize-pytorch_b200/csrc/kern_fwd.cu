@@ -20,6 +20,7 @@ KernelFn pick(int nw, bool init, int group) {
 }
 }  // namespace
 KernelFn get_fwd_kernel(int xdtype, int mode, int nw, bool init, int group) {
+    if (mode_relu(mode) || mode_add(mode)) return get_fwd_kernel_pre(mode, xdtype, nw, init, group);
     if (xdtype == DT_F64) return get_fwd_kernel_f64(nw, init, group);
     if (xdtype == DT_F32) return pick<float, M_FP32>(nw, init, group);
     if (xdtype == DT_BF16) return pick<__nv_bfloat16, M_FP32>(nw, init, group);

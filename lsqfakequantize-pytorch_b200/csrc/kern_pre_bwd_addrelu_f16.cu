@@ -1,0 +1,7 @@
+// kern_pre_bwd_addrelu_f16.cu -- backward kernels, fused prologue M_FP32_ADD_RELU, __half tensors (see kern_pre_bwd.inc).
+#define LSQ_PRE_MODE M_FP32_ADD_RELU
+#define LSQ_PRE_T __half
+#define LSQ_PRE_SUFFIX addrelu_f16
+#define LSQ_PRE_MINB kMinBlocksBwdAdd
+
+#include "kern_pre_bwd.inc"

@@ -1,0 +1,7 @@
+// kern_pre_bwd_relu_bf16.cu -- backward kernels, fused prologue M_FP32_RELU, __nv_bfloat16 tensors (see kern_pre_bwd.inc).
+#define LSQ_PRE_MODE M_FP32_RELU
+#define LSQ_PRE_T __nv_bfloat16
+#define LSQ_PRE_SUFFIX relu_bf16
+#define LSQ_PRE_MINB kMinBlocksBwd
+#define LSQ_PRE_COLUMN 1
+#include "kern_pre_bwd.inc"

@@ -1,0 +1,7 @@
+// kern_pre_bwd_relu_f32.cu -- backward kernels, fused prologue M_FP32_RELU, float tensors (see kern_pre_bwd.inc).
+#define LSQ_PRE_MODE M_FP32_RELU
+#define LSQ_PRE_T float
+#define LSQ_PRE_SUFFIX relu_f32
+#define LSQ_PRE_MINB kMinBlocksBwd
+#define LSQ_PRE_COLUMN 1
+#include "kern_pre_bwd.inc"

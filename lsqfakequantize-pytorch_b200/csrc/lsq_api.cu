@@ -47,13 +47,31 @@ const Tuning& tuning() {
 }
 
 // (x dtype, param dtype) -> arithmetic mode; returns -1 when the pair is not supported
-int pick_mode(int xdt, int pdt) {
+int pick_mode_plain(int xdt, int pdt) {
     if (xdt == DT_F32 && pdt == DT_F32) return M_FP32;
     if (xdt == DT_F16 && pdt == DT_F32) return M_FP32;
     if (xdt == DT_F16 && pdt == DT_F16) return M_HALF_EXACT;   // reference-exact c10::Half semantics
     if (xdt == DT_BF16 && (pdt == DT_F32 || pdt == DT_BF16)) return M_FP32;
     if (xdt == DT_F64 && pdt == DT_F64) return M_F64;           // reference rule: scale.dtype == x.dtype (lsq_cuda.cu:34-35)
     return -1;
+}
+// prologue fusion (LSQB200_PRE_RELU) exists for the fp32-internal arithmetic only: fp32 / fp16 / bf16 tensors with
+// fp32 (or, for bf16, bf16) parameters; the c10::Half-exact and float64 contracts mirror reference inputs and stay plain
+int pick_mode(int xdt, int pdt, int prologue = LSQB200_PRE_NONE) {
+    const int m = pick_mode_plain(xdt, pdt);
+    if (prologue == LSQB200_PRE_NONE || m < 0) return m;
+    if (m != M_FP32) return -1;
+    if (prologue == LSQB200_PRE_RELU) return M_FP32_RELU;
+    if (prologue == LSQB200_PRE_ADD_RELU) return M_FP32_ADD_RELU;
+    if (prologue == LSQB200_PRE_ADD) return M_FP32_ADD;
+    return -1;
+}
+bool prologue_known(int p) { return p == LSQB200_PRE_NONE || p == LSQB200_PRE_RELU || p == LSQB200_PRE_ADD_RELU || p == LSQB200_PRE_ADD; }
+bool prologue_adds(int p) { return p == LSQB200_PRE_ADD_RELU || p == LSQB200_PRE_ADD; }
+int check_prologue(int prologue, const void* x2, bool nonempty) {
+    if (!prologue_known(prologue)) return fail(LSQB200_ERR_ARG, "unknown prologue");
+    if (prologue_adds(prologue) && nonempty && !x2) return fail(LSQB200_ERR_ARG, "this prologue needs the second addend x2");
+    return 0;
 }
 
 int check_q(const lsqb200_qargs* q) {
@@ -118,9 +136,10 @@ int occupancy_of(const void* fn, int threads) {
     return occ;
 }
 
-ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_bytes, const Tuning& tn, int occ, bool backward) {
+ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_bytes, const Tuning& tn, int occ, bool backward,
+                    bool relu = false) {
     ColGeom g{};
-    const int ub = kColVariantNW[tn.col_variant] * 4;
+    const int ub = kColVariantNW[relu ? kColVariantRelu : tn.col_variant] * 4;
     const int es = elem_size(xdt), vec = ub / es;
     const long long L = C * inner;
     g.ok = tn.column_path && outer > 1 && C > 1 && C <= kMaxColumnChannels && L < (1LL << 31) && align_bytes % 16 == 0 && (L * es) % 16 == 0 &&
@@ -189,39 +208,46 @@ int launch_col(ColKernelFn k, const ColSeg& cs, const ColGeom& g, cudaStream_t s
     return 0;
 }
 
-int forward_common(const void* x, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
-                   int64_t inner, int xdt, int pdt, int per_channel, const lsqb200_qargs* q, void* stream) {
+int forward_common(const void* x, const void* x2, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
+                   int64_t inner, int xdt, int pdt, int per_channel, const lsqb200_qargs* q, int prologue, void* stream) {
     if (int r = check_q(q)) return r;
+    if (int r = check_prologue(prologue, x2, outer > 0 && C > 0 && inner > 0)) return r;
+    if (!prologue_adds(prologue)) x2 = nullptr;
     if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
     if (xdt < 0 || xdt > 3 || pdt < 0 || pdt > 3) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
-    const int mode = pick_mode(xdt, pdt);
-    if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
+    const int mode = pick_mode(xdt, pdt, prologue);
+    if (mode < 0) return fail(LSQB200_ERR_DTYPE, prologue ? "a fused prologue needs float32 / float16 / bfloat16 tensors with float32 scale / shift"
+                                                          : "unsupported (x dtype, scale/shift dtype) pair");
     if (outer * C * inner == 0) return 0;
     if (!x || !y || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
     if (xdt == DT_F64 && common_alignment({x, y, scale, shift}) < 8) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
-    if (per_channel && xdt != DT_F64) {
+    if (per_channel && xdt != DT_F64 && !mode_add(mode)) {
         ColKernelFn ck = get_col_fwd_kernel(xdt, mode, q->init_mode != 0, tuning().col_variant);
-        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, y}), tuning(), occupancy_of((const void*)ck, kColThreads), false);
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, y}), tuning(), occupancy_of((const void*)ck, kColThreads), false, mode_relu(mode));
         if (cg.ok) {
             const ColSeg cs = make_colseg(cg, x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, pdt, q, nullptr);
             return launch_col(ck, cs, cg, (cudaStream_t)stream);
         }
     }
-    const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, common_alignment({x, y}), tuning());
+    const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, common_alignment({x, x2, y}), tuning_for_mode(tuning(), mode));
     SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
+    a.x2 = x2;
     const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
     KernelFn k = get_fwd_kernel(xdt, mode, g.nw, q->init_mode != 0, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
-int backward_common(const void* grad, const void* x, void* gx, const void* scale, const void* shift, void* gscale,
+int backward_common(const void* grad, const void* x, const void* x2, void* gx, const void* scale, const void* shift, void* gscale,
                     void* gshift, int64_t outer, int64_t C, int64_t inner, int xdt, int pdt, int per_channel,
-                    const lsqb200_qargs* q, void* workspace, size_t wbytes, void* stream) {
+                    const lsqb200_qargs* q, int prologue, void* workspace, size_t wbytes, void* stream) {
     if (int r = check_q(q)) return r;
+    if (int r = check_prologue(prologue, x2, outer > 0 && C > 0 && inner > 0)) return r;
+    if (!prologue_adds(prologue)) x2 = nullptr;
     if (outer < 0 || C < 0 || inner < 0) return fail(LSQB200_ERR_ARG, "negative size");
     if (xdt < 0 || xdt > 3 || pdt < 0 || pdt > 3) return fail(LSQB200_ERR_DTYPE, "unknown dtype code");
-    const int mode = pick_mode(xdt, pdt);
-    if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair");
+    const int mode = pick_mode(xdt, pdt, prologue);
+    if (mode < 0) return fail(LSQB200_ERR_DTYPE, prologue ? "a fused prologue needs float32 / float16 / bfloat16 tensors with float32 scale / shift"
+                                                          : "unsupported (x dtype, scale/shift dtype) pair");
     if (!gscale || !gshift) return fail(LSQB200_ERR_ARG, "NULL grad_scale / grad_shift pointer");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nslot = per_channel ? C : 1;
@@ -236,14 +262,14 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
     if (!grad || !x || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
     if (xdt == DT_F64 && common_alignment({x, grad, gx, scale, shift, gscale, gshift}) < 8)
         return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
-    if (per_channel && xdt != DT_F64) {
+    if (per_channel && xdt != DT_F64 && !mode_add(mode)) {
         ColKernelFn ck = get_col_bwd_kernel(xdt, mode, bmode_of(q), tuning().col_variant);
-        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads), true);
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads), true, mode_relu(mode));
         if (cg.ok) {
             if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
                 return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
             const long long upr16 = C * inner * elem_size(xdt) / 16;
-            if (tuning().col_tma > 0 && upr16 >= kTmaConsumers) {
+            if (tuning().col_tma > 0 && upr16 >= kTmaConsumers && !mode_relu(mode)) {
                 // TMA-staged variant: a CTA owns 256 column units (4 KB of every row) and a contiguous run of rows
                 int smem = 0;
                 ColKernelFn tk = get_col_bwd_tma_kernel(xdt, mode, bmode_of(q), tuning().col_tma, &smem);
@@ -265,7 +291,7 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
             return launch_col(ck, cs, cg, st);
         }
     }
-    const Geometry g = plan_geometry(outer, C, inner, xdt, K_BWD, common_alignment({x, grad, gx}), tuning());
+    const Geometry g = plan_geometry(outer, C, inner, xdt, K_BWD, common_alignment({x, x2, grad, gx}), tuning_for_mode(tuning(), mode));
     double* partials = nullptr;
     unsigned* counters = nullptr;
     if (g.splits > 1) {
@@ -275,6 +301,7 @@ int backward_common(const void* grad, const void* x, void* gx, const void* scale
         partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kMaxCounters * 4);
     }
     SegArgs a = seg_args(x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, xdt, pdt, per_channel, q);
+    a.x2 = x2;
     const Seg seg = make_seg(a, g, partials, counters, 0);
     KernelFn k = get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, st);
@@ -341,13 +368,14 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
     const Tuning& tn = tuning();
     for (size_t i = 0; i < p->segs.size(); i++) {
         const lsqb200_segment& s = p->segs[i];
-        const int mode = pick_mode(s.xdtype, s.pdtype);
-        if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype) pair in plan");
+        const int mode = pick_mode(s.xdtype, s.pdtype, s.prologue);
+        if (mode < 0) return fail(LSQB200_ERR_DTYPE, "unsupported (x dtype, scale/shift dtype, prologue) combination in plan");
         if (s.outer * s.C * s.inner == 0) continue;
         int al = common_alignment({s.x});
-        if (kind == K_FWD) al = common_alignment({s.x, s.y});
-        if (kind == K_BWD) al = common_alignment({s.x, s.grad, s.gx});
-        Geometry g = plan_geometry(s.outer, s.C, s.inner, s.xdtype, kind, al, tn);
+        const void* sx2 = prologue_adds(s.prologue) ? s.x2 : nullptr;
+        if (kind == K_FWD) al = common_alignment({s.x, sx2, s.y});
+        if (kind == K_BWD) al = common_alignment({s.x, sx2, s.grad, s.gx});
+        Geometry g = plan_geometry(s.outer, s.C, s.inner, s.xdtype, kind, al, tuning_for_mode(tn, mode));
         int variant = 0;
         KernelFn k = nullptr;
         if (kind == K_FWD) { variant = s.q.init_mode != 0; k = get_fwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
@@ -378,6 +406,7 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         }
         SegArgs a = seg_args(s.x, s.y, s.grad, s.gx, s.scale, s.shift, s.gscale, s.gshift, s.outer, s.C, s.inner,
                              s.xdtype, s.pdtype, s.per_channel, &s.q);
+        a.x2 = sx2;
         Seg seg = make_seg(a, g, partials, counters, c.tiles);
         seg.stats_out = nullptr;   // patched per run for stats
         // tag for stats runs: remember which public segment this is (reuse chan_stride, unused by kernels)
@@ -491,25 +520,45 @@ int lsqb200_query_launch(int64_t outer, int64_t C, int64_t inner, int xdtype, in
 
 int lsqb200_fwd_tensor(const void* x, void* y, const void* scale, const void* shift, int64_t numel, int xdtype,
                        int pdtype, const lsqb200_qargs* q, void* stream) {
-    return forward_common(x, y, scale, shift, 1, 1, numel, xdtype, pdtype, 0, q, stream);
+    return forward_common(x, nullptr, y, scale, shift, 1, 1, numel, xdtype, pdtype, 0, q, LSQB200_PRE_NONE, stream);
+}
+int lsqb200_fwd_tensor_pre(const void* x, const void* x2, void* y, const void* scale, const void* shift, int64_t numel, int xdtype,
+                           int pdtype, const lsqb200_qargs* q, int prologue, void* stream) {
+    return forward_common(x, x2, y, scale, shift, 1, 1, numel, xdtype, pdtype, 0, q, prologue, stream);
 }
 
 int lsqb200_bwd_tensor(const void* grad, const void* x, void* gx, const void* scale, const void* shift, void* gscale,
                        void* gshift, int64_t numel, int xdtype, int pdtype, const lsqb200_qargs* q, void* workspace,
                        size_t workspace_bytes, void* stream) {
-    return backward_common(grad, x, gx, scale, shift, gscale, gshift, 1, 1, numel, xdtype, pdtype, 0, q, workspace,
+    return backward_common(grad, x, nullptr, gx, scale, shift, gscale, gshift, 1, 1, numel, xdtype, pdtype, 0, q, LSQB200_PRE_NONE, workspace,
+                           workspace_bytes, stream);
+}
+int lsqb200_bwd_tensor_pre(const void* grad, const void* x, const void* x2, void* gx, const void* scale, const void* shift, void* gscale,
+                           void* gshift, int64_t numel, int xdtype, int pdtype, const lsqb200_qargs* q, int prologue,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    return backward_common(grad, x, x2, gx, scale, shift, gscale, gshift, 1, 1, numel, xdtype, pdtype, 0, q, prologue, workspace,
                            workspace_bytes, stream);
 }
 
 int lsqb200_fwd_channel(const void* x, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
                         int64_t inner, int xdtype, int pdtype, const lsqb200_qargs* q, void* stream) {
-    return forward_common(x, y, scale, shift, outer, C, inner, xdtype, pdtype, 1, q, stream);
+    return forward_common(x, nullptr, y, scale, shift, outer, C, inner, xdtype, pdtype, 1, q, LSQB200_PRE_NONE, stream);
+}
+int lsqb200_fwd_channel_pre(const void* x, const void* x2, void* y, const void* scale, const void* shift, int64_t outer, int64_t C,
+                            int64_t inner, int xdtype, int pdtype, const lsqb200_qargs* q, int prologue, void* stream) {
+    return forward_common(x, x2, y, scale, shift, outer, C, inner, xdtype, pdtype, 1, q, prologue, stream);
 }
 
 int lsqb200_bwd_channel(const void* grad, const void* x, void* gx, const void* scale, const void* shift, void* gscale,
                         void* gshift, int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype,
                         const lsqb200_qargs* q, void* workspace, size_t workspace_bytes, void* stream) {
-    return backward_common(grad, x, gx, scale, shift, gscale, gshift, outer, C, inner, xdtype, pdtype, 1, q, workspace,
+    return backward_common(grad, x, nullptr, gx, scale, shift, gscale, gshift, outer, C, inner, xdtype, pdtype, 1, q, LSQB200_PRE_NONE, workspace,
+                           workspace_bytes, stream);
+}
+int lsqb200_bwd_channel_pre(const void* grad, const void* x, const void* x2, void* gx, const void* scale, const void* shift, void* gscale,
+                            void* gshift, int64_t outer, int64_t C, int64_t inner, int xdtype, int pdtype,
+                            const lsqb200_qargs* q, int prologue, void* workspace, size_t workspace_bytes, void* stream) {
+    return backward_common(grad, x, x2, gx, scale, shift, gscale, gshift, outer, C, inner, xdtype, pdtype, 1, q, prologue, workspace,
                            workspace_bytes, stream);
 }
 
@@ -624,9 +673,10 @@ int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan*
     cudaGetDevice(&p->device);
     long long off = 0;
     for (const auto& s : p->segs) {
-        if (s.outer < 0 || s.C < 0 || s.inner < 0 || s.xdtype < 0 || s.xdtype > 3 || s.pdtype < 0 || s.pdtype > 3) {
+        if (s.outer < 0 || s.C < 0 || s.inner < 0 || s.xdtype < 0 || s.xdtype > 3 || s.pdtype < 0 || s.pdtype > 3 ||
+            !prologue_known(s.prologue) || (prologue_adds(s.prologue) && !s.x2 && s.outer * s.C * s.inner != 0)) {
             delete p;
-            return fail(LSQB200_ERR_PLAN, "bad segment (negative size or unknown dtype)");
+            return fail(LSQB200_ERR_PLAN, "bad segment (negative size, unknown dtype, unknown prologue or missing x2)");
         }
         p->stats_offset.push_back(off);
         off += s.per_channel ? s.C : 1;

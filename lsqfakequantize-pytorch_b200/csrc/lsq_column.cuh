@@ -97,6 +97,7 @@ template <typename T, int MODE, bool INIT, int CNW, int kColUnroll, int MINB, in
 __global__ void __launch_bounds__(kColThreads, MINB)
 lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
     constexpr int NW = CNW, VEC = ColVec<T, CNW>::VEC, UB = CNW * 4;
+    constexpr bool RAWCOPY = INIT && !mode_relu(MODE);
     asm volatile("griddepcontrol.launch_dependents;");
     const int tx = threadIdx.x % cs.tx, ty = threadIdx.x / cs.tx;
     const long long uc = (long long)blockIdx.x * cs.tx + tx;
@@ -116,23 +117,23 @@ lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
         for (int r = 0; r < kColUnroll; r++) xr[r] = ld_unit<LD, NW>(px + r * w.stride);
 #pragma unroll
         for (int r = 0; r < kColUnroll; r++) {
-            if (INIT) { st_unit<ST, NW>(py + r * w.stride, xr[r]); continue; }
+            if (RAWCOPY) { st_unit<ST, NW>(py + r * w.stride, xr[r]); continue; }
             float f[VEC];
             unpack_unit<T, NW>(xr[r], f);
 #pragma unroll
-            for (int k = 0; k < VEC; k++) f[k] = fq_forward<MODE>(f[k], sp.chan(k, cs));
+            for (int k = 0; k < VEC; k++) f[k] = INIT ? pre_op<MODE>(f[k]) : fq_forward<MODE>(f[k], sp.chan(k, cs));
             st_unit<ST, NW>(py + r * w.stride, pack_unit<T, NW>(f));
         }
         px += kColUnroll * w.stride; py += kColUnroll * w.stride;
     }
     for (; cnt > 0; cnt--) {
         const Raw<NW> xr = ld_unit<LD, NW>(px);
-        if (INIT) st_unit<ST, NW>(py, xr);
+        if (RAWCOPY) st_unit<ST, NW>(py, xr);
         else {
             float f[VEC];
             unpack_unit<T, NW>(xr, f);
 #pragma unroll
-            for (int k = 0; k < VEC; k++) f[k] = fq_forward<MODE>(f[k], sp.chan(k, cs));
+            for (int k = 0; k < VEC; k++) f[k] = INIT ? pre_op<MODE>(f[k]) : fq_forward<MODE>(f[k], sp.chan(k, cs));
             st_unit<ST, NW>(py, pack_unit<T, NW>(f));
         }
         px += w.stride; py += w.stride;
@@ -180,7 +181,7 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
             for (int k = 0; k < VEC; k++)
                 fg[k] = fq_backward<MODE, BMODE, false>(fg[k], fx[k], sp.chan(k, cs), accS[k], accB[k]);
             if (dst) {
-                if (bmode_passthrough(BMODE)) st_unit<ST, NW>(dst, gr);
+                if (bmode_passthrough(BMODE) && !mode_relu(MODE)) st_unit<ST, NW>(dst, gr);
                 else st_unit<ST, NW>(dst, pack_unit<T, NW>(fg));
             }
         };
@@ -364,7 +365,7 @@ lsq_col_bwd_tma_kernel(const __grid_constant__ ColSeg cs) {
             for (int k = 0; k < VEC; k++)
                 fg[k] = fq_backward<MODE, BMODE, false>(fg[k], fx[k], sp.chan(k, cs), accS[k], accB[k]);
             if (pgx) {
-                if (bmode_passthrough(BMODE)) st_unit<ST, NW>(pgx, gr);
+                if (bmode_passthrough(BMODE) && !mode_relu(MODE)) st_unit<ST, NW>(pgx, gr);
                 else st_unit<ST, NW>(pgx, pack_unit<T, NW>(fg));
                 pgx += row_pitch;
             }
@@ -445,6 +446,13 @@ ColKernelFn get_col_fwd_kernel(int xdtype, int mode, bool init, int variant);
 ColKernelFn get_col_bwd_kernel(int xdtype, int mode, int bmode, int variant);
 // TMA-staged backward: tma_variant 1 = (R 4 rows, S 3 stages, 96 KB ring), 2 = (2, 4, 64 KB), 3 = (8, 3, 192 KB); sets *smem_bytes
 ColKernelFn get_col_bwd_tma_kernel(int xdtype, int mode, int bmode, int tma_variant, int* smem_bytes);
+// kern_pre_*_relu*.cu: MODE = M_FP32_RELU, default variant only (the variant knob is an experiment switch of the plain
+// kernels).  The two-operand ADD prologues have no column-layout kernels: short channel rows take the row-tiled path.
+ColKernelFn get_col_fwd_kernel_pre_relu(int xdtype, bool init);
+ColKernelFn get_col_bwd_kernel_pre_relu_f32(int bmode);
+ColKernelFn get_col_bwd_kernel_pre_relu_f16(int bmode);
+ColKernelFn get_col_bwd_kernel_pre_relu_bf16(int bmode);
+constexpr int kColVariantRelu = 1;
 // variant -> (unit words, rows in flight, min CTAs/SM); index with Tuning::col_variant
 constexpr int kColVariants = 6;
 constexpr int kColVariantNW[kColVariants] = {4, 4, 2, 2, 4, 4};

@@ -31,7 +31,18 @@ enum : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_F64 = 3 };   // DT_F64: lsq
 // MODE: how the affine value v = x/s + zp is formed
 enum : int { M_FP32 = 0,        // fp32 internal math (fp32 tensors; fp16/bf16 tensors up-cast)
              M_HALF_EXACT = 1,  // fp16 x with fp16 params: round to half after every operator (c10::Half)
-             M_F64 = 2 };       // float64 x with float64 params (lsq_f64.cuh)
+             M_F64 = 2,         // float64 x with float64 params (lsq_f64.cuh)
+             M_FP32_RELU = 3,      // M_FP32 with the ReLU prologue fused in: fake-quant of relu(x) in one pass
+             M_FP32_ADD_RELU = 4,  // ... of relu(x + x2): the residual join of a ResNet block
+             M_FP32_ADD = 5 };     // ... of x + x2
+// Prologue fusion (not in the reference: there `relu` is a separate ATen pass that writes relu(x) to HBM and the
+// fake-quant reads it back).  lsq(relu(x)): forward x' = relu(x) feeds fq_forward; backward the upstream gradient
+// goes through the fake-quant's mask on x' and then through relu's own backward (threshold_backward: x <= 0 -> exact 0).
+// With an ADD prologue the fake-quant's input is the residual sum x + x2 ROUNDED TO THE TENSOR TYPE (what ATen's add
+// writes and the next op reads back), so results stay bit-identical to the three-pass sequence; the single grad_x the
+// backward writes is the gradient of both addends.
+__host__ __device__ constexpr bool mode_relu(int m) { return m == M_FP32_RELU || m == M_FP32_ADD_RELU; }
+__host__ __device__ constexpr bool mode_add(int m) { return m == M_FP32_ADD_RELU || m == M_FP32_ADD; }
 enum : int { B_NORMAL = 0, B_INIT = 1, B_EVAL = 2, B_EVAL_INIT = 3 };
 __host__ __device__ constexpr bool bmode_passthrough(int b) { return b == B_INIT || b == B_EVAL_INIT; }
 __host__ __device__ constexpr bool bmode_reduces(int b) { return b == B_NORMAL || b == B_INIT; }
@@ -42,6 +53,7 @@ __host__ __device__ constexpr bool bmode_reduces(int b) { return b == B_NORMAL |
 // ---------------------------------------------------------------------------------------------
 struct Seg {
     const void* x;
+    const void* x2;        // second addend (ADD prologues), same layout as x; else unused
     void* y;
     const void* g;
     void* gx;
@@ -189,6 +201,12 @@ __device__ __forceinline__ Raw<NW> pack_unit(const float* f) {
     return r;
 }
 
+// residual sum as ATen's add kernel forms it: fp32 add, one rounding to the tensor type
+template <typename T>
+__device__ __forceinline__ float pre_add(float a, float b) {
+    return ElemTraits<T>::to_f(ElemTraits<T>::from_f(__fadd_rn(a, b)));
+}
+
 __device__ __forceinline__ float load_param(const void* p, long long i, int pdt) {
     if (pdt == DT_F32) return reinterpret_cast<const float*>(p)[i];
     if (pdt == DT_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
@@ -210,6 +228,13 @@ struct Chan {
 };
 
 __device__ __forceinline__ float hround(float f) { return __half2float(__float2half_rn(f)); }
+
+// torch.relu == clamp_min(x, 0): NaN stays NaN, -0 and every negative become +0 (max.NaN orders -0 < +0)
+template <int MODE>
+__device__ __forceinline__ float pre_op(float x) {
+    if (mode_relu(MODE)) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(0.0f)); return r; }
+    return x;
+}
 
 template <int MODE>
 __device__ __forceinline__ Chan make_chan(float scale, float shift, const Seg& sg) {
@@ -261,7 +286,8 @@ __device__ __forceinline__ float affine_v(float x, const Chan& c) {
 }
 
 template <int MODE>
-__device__ __forceinline__ float fq_forward(float x, const Chan& c) {
+__device__ __forceinline__ float fq_forward(float x_in, const Chan& c) {
+    const float x = pre_op<MODE>(x_in);
     const float v = affine_v<MODE>(x, c);
     const float r = rintf(fminf(c.qmax, fmaxf(c.qmin, v)));       // max first: NaN -> qmin
     return __fmul_rn(__fsub_rn(r, c.zp), c.s);
@@ -284,11 +310,13 @@ __device__ __forceinline__ float fq_forward(float x, const Chan& c) {
 // few terms are summed and nothing averages the 2-ulp difference out); ACC is the accumulator
 // type (float partials are promoted to double after <= 32-64 terms).
 template <int MODE, int BMODE, bool EXACT, typename ACC>
-__device__ __forceinline__ float fq_backward(float g, float x, const Chan& c, ACC& accS, ACC& accB) {
+__device__ __forceinline__ float fq_backward(float g, float x_in, const Chan& c, ACC& accS, ACC& accB) {
+    const float x = pre_op<MODE>(x_in);                                // fused prologue: the fake-quant sees relu(x)
     const float v = affine_v<MODE>(x, c);
     const bool mask = (v > c.qmin) && (v < c.qmax);
     const float m = mask ? 1.0f : 0.0f;
-    const float dX = bmode_passthrough(BMODE) ? g : __fmul_rn(g, m);   // g*mask keeps -0 / NaN like the reference
+    float dX = bmode_passthrough(BMODE) ? g : __fmul_rn(g, m);         // g*mask keeps -0 / NaN like the reference
+    if (mode_relu(MODE)) dX = (x <= 0.0f) ? 0.0f : dX;                 // relu backward (threshold_backward): exact 0, NaN x passes
     if (bmode_reduces(BMODE)) {
         const float xq = fmaxf(fminf(v, c.qmax), c.qmin);          // min first: NaN -> qmax
         const float t = __fsub_rn(rintf(xq), c.zp);
@@ -483,6 +511,8 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     constexpr int VEC = UnitOf<T, NW>::VEC;
     constexpr int UB = NW * 4;   // unit bytes
     constexpr int GROUPS = THREADS / G;
+    constexpr bool RAWCOPY = INIT && !mode_relu(MODE) && !mode_add(MODE);   // learned init: y is x's bits (lsq_kernel.h:13) unless a prologue is fused in
+    constexpr bool ADD = mode_add(MODE);
     __shared__ Seg smem_seg[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
     constexpr int ROWS = tiles_per_group(G);
@@ -495,6 +525,7 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const Seg& sg = smem_seg[grp];
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    const T* __restrict__ x2p = reinterpret_cast<const T*>(sg.x2);
     T* __restrict__ yp = reinterpret_cast<T*>(sg.y);
     Walker w;
     w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
@@ -505,7 +536,9 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
-            yp[e] = INIT ? xp[e] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xp[e]), lch.get(sg)));
+            const float xin = ADD ? pre_add<T>(Tr::to_f(xp[e]), Tr::to_f(x2p[e])) : Tr::to_f(xp[e]);
+            if constexpr (INIT) yp[e] = RAWCOPY ? xp[e] : Tr::from_f(pre_op<MODE>(xin));
+            else yp[e] = Tr::from_f(fq_forward<MODE>(xin, lch.get(sg)));
         }
     }
     while (w.more()) {
@@ -514,29 +547,46 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
 #pragma unroll
         for (int k = 0; k < UNROLL; k++) ok[k] = w.next(addr[k]);
         if constexpr (VEC > 1) {
-            Raw<NW> xr[UNROLL];
+            Raw<NW> xr[UNROLL], x2r[ADD ? UNROLL : 1];
 #pragma unroll
-            for (int k = 0; k < UNROLL; k++)   // tail lanes re-read unit 0 (always valid) so loads stay unconditional
+            for (int k = 0; k < UNROLL; k++) { // tail lanes re-read unit 0 (always valid) so loads stay unconditional
                 xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + (ok[k] ? addr[k] : addr[0]) * UB);
+                if constexpr (ADD) x2r[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(x2p) + (ok[k] ? addr[k] : addr[0]) * UB);
+            }
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
-                if (INIT) { st_unit<ST, NW>(reinterpret_cast<char*>(yp) + addr[k] * UB, xr[k]); continue; }
-                const Chan& ch = lch.get(sg);
+                if (RAWCOPY) { st_unit<ST, NW>(reinterpret_cast<char*>(yp) + addr[k] * UB, xr[k]); continue; }
                 float f[VEC];
                 unpack_unit<T, NW>(xr[k], f);
+                if constexpr (ADD) {
+                    float f2[VEC];
+                    unpack_unit<T, NW>(x2r[k], f2);
 #pragma unroll
-                for (int e = 0; e < VEC; e++) f[e] = fq_forward<MODE>(f[e], ch);
+                    for (int e = 0; e < VEC; e++) f[e] = pre_add<T>(f[e], f2[e]);
+                }
+                if constexpr (INIT) {                   // learned init behind a fused prologue: y = relu(x)
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) f[e] = pre_op<MODE>(f[e]);
+                } else {
+                    const Chan& ch = lch.get(sg);
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) f[e] = fq_forward<MODE>(f[e], ch);
+                }
                 st_unit<ST, NW>(reinterpret_cast<char*>(yp) + addr[k] * UB, pack_unit<T, NW>(f));
             }
         } else {
-            T xr[UNROLL];
+            T xr[UNROLL], x2r[ADD ? UNROLL : 1];
 #pragma unroll
             for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) xr[k] = xp[addr[k]];
+                if (ok[k]) { xr[k] = xp[addr[k]]; if constexpr (ADD) x2r[k] = x2p[addr[k]]; }
 #pragma unroll
             for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) yp[addr[k]] = INIT ? xr[k] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xr[k]), lch.get(sg)));
+                if (ok[k]) {
+                    const float xin = ADD ? pre_add<T>(Tr::to_f(xr[k]), Tr::to_f(x2r[ADD ? k : 0])) : Tr::to_f(xr[k]);
+                    if constexpr (INIT) yp[addr[k]] = RAWCOPY ? xr[k] : Tr::from_f(pre_op<MODE>(xin));
+                    else yp[addr[k]] = Tr::from_f(fq_forward<MODE>(xin, lch.get(sg)));
+                }
         }
     }
     }   // tiles of this group
@@ -583,6 +633,8 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     constexpr int VEC = UnitOf<T, NW>::VEC;
     constexpr int UB = NW * 4;   // unit bytes
     constexpr int GROUPS = THREADS / G;
+    constexpr bool RAWPASS = bmode_passthrough(BMODE) && !mode_relu(MODE);   // learned init: gx is grad's bits (lsq_kernel.h:35)
+    constexpr bool ADD = mode_add(MODE);
     __shared__ Seg smem_seg[GROUPS];
     __shared__ double red[64];
     __shared__ int last_flag[GROUPS];
@@ -597,6 +649,7 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const Seg& sg = smem_seg[grp];
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    const T* __restrict__ x2p = reinterpret_cast<const T*>(sg.x2);
     const T* __restrict__ gp = reinterpret_cast<const T*>(sg.g);
     T* __restrict__ gxp = reinterpret_cast<T*>(sg.gx);
     const bool write_gx = gxp != nullptr;
@@ -610,8 +663,9 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
             const long long e = i < tl.peel_n0 ? tl.peel_begin0 + i : tl.peel_begin1 + (i - tl.peel_n0);
-            const float dx = fq_backward<MODE, BMODE, true>(Tr::to_f(gp[e]), Tr::to_f(xp[e]), lch.get(sg), accS, accB);
-            if (write_gx) gxp[e] = bmode_passthrough(BMODE) ? gp[e] : Tr::from_f(dx);
+            const float xin = ADD ? pre_add<T>(Tr::to_f(xp[e]), Tr::to_f(x2p[e])) : Tr::to_f(xp[e]);
+            const float dx = fq_backward<MODE, BMODE, true>(Tr::to_f(gp[e]), xin, lch.get(sg), accS, accB);
+            if (write_gx) gxp[e] = RAWPASS ? gp[e] : Tr::from_f(dx);
         }
     }
     while (w.more()) {
@@ -624,11 +678,12 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
         using Acc = typename std::conditional<G == 32, double, float>::type;
         Acc ls = 0, lb = 0;
         if constexpr (VEC > 1) {
-            Raw<NW> xr[UNROLL], gr[UNROLL];
+            Raw<NW> xr[UNROLL], gr[UNROLL], x2r[ADD ? UNROLL : 1];
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {   // tail lanes re-read unit 0 (always valid) so loads stay unconditional
                 const long long a = ok[k] ? addr[k] : addr[0];
                 xr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(xp) + a * UB);
+                if constexpr (ADD) x2r[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(x2p) + a * UB);
                 gr[k] = ld_unit<LD, NW>(reinterpret_cast<const char*>(gp) + a * UB);
             }
 #pragma unroll
@@ -637,24 +692,31 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
                 const Chan& ch = lch.get(sg);
                 float fx[VEC], fg[VEC];
                 unpack_unit<T, NW>(xr[k], fx);
+                if constexpr (ADD) {
+                    float f2[VEC];
+                    unpack_unit<T, NW>(x2r[k], f2);
+#pragma unroll
+                    for (int e = 0; e < VEC; e++) fx[e] = pre_add<T>(fx[e], f2[e]);
+                }
                 unpack_unit<T, NW>(gr[k], fg);
 #pragma unroll
                 for (int e = 0; e < VEC; e++) fg[e] = fq_backward<MODE, BMODE, G == 32>(fg[e], fx[e], ch, ls, lb);
                 if (write_gx) {
-                    if (bmode_passthrough(BMODE)) st_unit<ST, NW>(reinterpret_cast<char*>(gxp) + addr[k] * UB, gr[k]);
+                    if (RAWPASS) st_unit<ST, NW>(reinterpret_cast<char*>(gxp) + addr[k] * UB, gr[k]);
                     else st_unit<ST, NW>(reinterpret_cast<char*>(gxp) + addr[k] * UB, pack_unit<T, NW>(fg));
                 }
             }
         } else {
-            T xr[UNROLL], gr[UNROLL];
+            T xr[UNROLL], gr[UNROLL], x2r[ADD ? UNROLL : 1];
 #pragma unroll
             for (int k = 0; k < UNROLL; k++)
-                if (ok[k]) { xr[k] = xp[addr[k]]; gr[k] = gp[addr[k]]; }
+                if (ok[k]) { xr[k] = xp[addr[k]]; gr[k] = gp[addr[k]]; if constexpr (ADD) x2r[k] = x2p[addr[k]]; }
 #pragma unroll
             for (int k = 0; k < UNROLL; k++) {
                 if (!ok[k]) continue;
-                const float dx = fq_backward<MODE, BMODE, G == 32>(Tr::to_f(gr[k]), Tr::to_f(xr[k]), lch.get(sg), ls, lb);
-                if (write_gx) gxp[addr[k]] = bmode_passthrough(BMODE) ? gr[k] : Tr::from_f(dx);
+                const float xin = ADD ? pre_add<T>(Tr::to_f(xr[k]), Tr::to_f(x2r[ADD ? k : 0])) : Tr::to_f(xr[k]);
+                const float dx = fq_backward<MODE, BMODE, G == 32>(Tr::to_f(gr[k]), xin, lch.get(sg), ls, lb);
+                if (write_gx) gxp[addr[k]] = RAWPASS ? gr[k] : Tr::from_f(dx);
             }
         }
         accS += (double)ls; accB += (double)lb;

@@ -56,7 +56,32 @@ KernelFn get_bwd_kernel_f32(int mode, int nw, int bmode, int group);
 KernelFn get_bwd_kernel_f16_mixed(int mode, int nw, int bmode, int group);
 KernelFn get_bwd_kernel_f16_exact(int mode, int nw, int bmode, int group);
 KernelFn get_bwd_kernel_bf16(int mode, int nw, int bmode, int group);
+// kern_pre_*.cu: fused prologues (MODE = M_FP32_RELU / M_FP32_ADD_RELU / M_FP32_ADD: fake-quant of relu(x), relu(x + x2),
+// x + x2 in one pass); fp32 / fp16 / bf16 tensors, fp32-internal arithmetic
+#define LSQ_DECL_PRE(P)                                                   \
+    KernelFn get_fwd_kernel_pre_##P(int xdtype, int nw, bool init, int group); \
+    KernelFn get_bwd_kernel_pre_##P##_f32(int nw, int bmode, int group);   \
+    KernelFn get_bwd_kernel_pre_##P##_f16(int nw, int bmode, int group);   \
+    KernelFn get_bwd_kernel_pre_##P##_bf16(int nw, int bmode, int group);
+LSQ_DECL_PRE(relu)
+LSQ_DECL_PRE(addrelu)
+LSQ_DECL_PRE(add)
+#undef LSQ_DECL_PRE
+inline KernelFn get_fwd_kernel_pre(int mode, int xdtype, int nw, bool init, int group) {
+    if (mode == M_FP32_RELU) return get_fwd_kernel_pre_relu(xdtype, nw, init, group);
+    if (mode == M_FP32_ADD_RELU) return get_fwd_kernel_pre_addrelu(xdtype, nw, init, group);
+    return get_fwd_kernel_pre_add(xdtype, nw, init, group);
+}
+inline KernelFn get_bwd_kernel_pre(int mode, int xdtype, int nw, int bmode, int group) {
+#define LSQ_PICK_PRE(P) (xdtype == DT_F32 ? get_bwd_kernel_pre_##P##_f32(nw, bmode, group) \
+                         : (xdtype == DT_F16 ? get_bwd_kernel_pre_##P##_f16(nw, bmode, group) : get_bwd_kernel_pre_##P##_bf16(nw, bmode, group)))
+    if (mode == M_FP32_RELU) return LSQ_PICK_PRE(relu);
+    if (mode == M_FP32_ADD_RELU) return LSQ_PICK_PRE(addrelu);
+    return LSQ_PICK_PRE(add);
+#undef LSQ_PICK_PRE
+}
 inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int group) {
+    if (mode_relu(mode) || mode_add(mode)) return get_bwd_kernel_pre(mode, xdtype, nw, bmode, group);
     if (xdtype == DT_F64) return get_bwd_kernel_f64(nw, bmode, group);
     if (xdtype == DT_F32) return get_bwd_kernel_f32(mode, nw, bmode, group);
     if (xdtype == DT_F16) return mode == M_HALF_EXACT ? get_bwd_kernel_f16_exact(mode, nw, bmode, group)
@@ -107,7 +132,20 @@ struct Tuning {
     int whole_waves = 1;        // round big-tensor tile counts to whole waves of resident CTAs
     int pdl = 1;                // launch with programmatic stream serialization (prologue overlaps predecessor's tail)
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
+    // resident CTAs/SM the kernel family really gets (its __launch_bounds__): whole-wave rounding uses these.  The two-operand
+    // ADD prologues run with 4 / 3 (tuning_for_mode below)
+    int fwd_resident = kMinBlocksFwd;
+    int bwd_resident = kMinBlocksBwd;
 };
+constexpr int kMinBlocksFwdAdd = 4, kMinBlocksBwdAdd = 3;   // LSQ_PRE_MINB of kern_pre_*_add*.cu
+inline Tuning tuning_for_mode(const Tuning& tn, int mode) {
+    if (!mode_add(mode)) return tn;
+    Tuning t = tn;
+    t.fwd_resident = kMinBlocksFwdAdd; t.bwd_resident = kMinBlocksBwdAdd;
+    if (t.fwd_min_tiles_per_sm > kMinBlocksFwdAdd) t.fwd_min_tiles_per_sm = kMinBlocksFwdAdd;
+    if (t.bwd_min_tiles_per_sm > kMinBlocksBwdAdd) t.bwd_min_tiles_per_sm = kMinBlocksBwdAdd;
+    return t;
+}
 
 enum : int { K_FWD = 0, K_BWD = 1, K_STATS = 2 };
 
@@ -160,7 +198,7 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
     // whole waves: when a channel is cut into more tiles than fit on the machine at once, round
     // the count up to a multiple of the resident CTA slots so the last wave is full
     if (C == 1) {
-        const long long resident = (long long)tn.sm_count * (kind == K_BWD ? kMinBlocksBwd : (kind == K_FWD ? kMinBlocksFwd : kResidentStats));
+        const long long resident = (long long)tn.sm_count * (kind == K_BWD ? tn.bwd_resident : (kind == K_FWD ? tn.fwd_resident : kResidentStats));
         if (tn.whole_waves && splits > resident) {
             const long long r = (splits + resident - 1) / resident * resident;
             if (r <= max_splits) splits = r;
@@ -194,6 +232,7 @@ inline Geometry plan_geometry(long long outer, long long C, long long inner, int
 }
 
 struct SegArgs {
+    const void* x2;        // second addend of the ADD prologues (else nullptr)
     const void* x; void* y; const void* g; void* gx;
     const void* scale; const void* shift; void* gscale; void* gshift;
     float* stats_out;
@@ -214,7 +253,7 @@ inline int common_alignment(std::initializer_list<const void*> ps) {
 inline Seg make_seg(const SegArgs& a, const Geometry& g, double* partials, unsigned* counters, long long tile_begin) {
     Seg s;
     std::memset(&s, 0, sizeof(s));
-    s.x = a.x; s.y = a.y; s.g = a.g; s.gx = a.gx;
+    s.x = a.x; s.x2 = a.x2; s.y = a.y; s.g = a.g; s.gx = a.gx;
     s.scale = a.scale; s.shift = a.shift; s.gscale = a.gscale; s.gshift = a.gshift;
     s.partials = partials; s.counters = counters; s.stats_out = a.stats_out;
     s.C = g.C; s.vpr = g.vpr; s.row_stride = g.row_stride; s.chan_stride = g.vpr;

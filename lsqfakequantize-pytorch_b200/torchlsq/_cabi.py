@@ -13,6 +13,7 @@ from pathlib import Path
 LIB_NAME = "libtorchlsq_b200.so"
 F32, F16, BF16, F64 = 0, 1, 2, 3
 SEM_LSQ, SEM_TORCH, SEM_TORCH_CPU = 0, 1, 2
+PRE_NONE, PRE_RELU, PRE_ADD_RELU, PRE_ADD = 0, 1, 2, 3   # fused prologue in front of the fake-quant (lsqb200_*_pre)
 
 
 class QArgs(Structure):
@@ -27,8 +28,8 @@ class Segment(Structure):
     _fields_ = [("x", c_void_p), ("y", c_void_p), ("grad", c_void_p), ("gx", c_void_p),
                 ("scale", c_void_p), ("shift", c_void_p), ("gscale", c_void_p), ("gshift", c_void_p),
                 ("outer", c_int64), ("C", c_int64), ("inner", c_int64),
-                ("xdtype", c_int32), ("pdtype", c_int32), ("per_channel", c_int32), ("reserved", c_int32),
-                ("q", QArgs)]
+                ("xdtype", c_int32), ("pdtype", c_int32), ("per_channel", c_int32), ("prologue", c_int32),
+                ("q", QArgs), ("x2", c_void_p)]
 
 
 class ObserverArgs(Structure):
@@ -66,6 +67,15 @@ _PROTOTYPES = {
     "lsqb200_bwd_channel": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_int64, c_int64, c_int64, c_int, c_int, POINTER(QArgs),
                                     c_void_p, c_size_t, c_void_p]),
+    "lsqb200_fwd_tensor_pre": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                       POINTER(QArgs), c_int, c_void_p]),
+    "lsqb200_bwd_tensor_pre": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int, c_int, POINTER(QArgs), c_int, c_void_p, c_size_t, c_void_p]),
+    "lsqb200_fwd_channel_pre": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                        c_int, c_int, POINTER(QArgs), c_int, c_void_p]),
+    "lsqb200_bwd_channel_pre": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int64, c_int64, c_int64, c_int, c_int, POINTER(QArgs), c_int,
+                                        c_void_p, c_size_t, c_void_p]),
     "lsqb200_weight_init_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int,
                                           c_int64, c_int64, c_void_p, c_size_t, c_void_p]),
     "lsqb200_observe": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -160,26 +160,47 @@ def _qargs(*scalars):
     return q
 
 
+def _addend_ptr(x2, xd):
+    """Device pointer of the second addend of an ADD prologue, which must share x's dense layout (the kernels walk both
+    with one index); None without one."""
+    if x2 is None:
+        return None
+    if x2.shape != xd.shape or x2.stride() != xd.stride() or x2.dtype != xd.dtype or x2.device != xd.device:
+        raise RuntimeError("the two addends must have the same shape, strides, dtype and device")
+    return x2.data_ptr()
+
+
+def _check_prologue(x, scale):
+    if x.dtype == torch.float64 or (x.dtype == torch.float16 and scale.dtype == torch.float16):
+        raise RuntimeError("fused-prologue lsq needs float32 / float16 / bfloat16 input with float32 scale / shift "
+                           "(float64 and all-float16 calls mirror reference inputs and have no fused prologue)")
+
+
 def _fwd_tensor_cuda(x, scale, shift, quant_min, quant_max, type_min, type_max,
-                     use_grad_scaling, grad_scaler, sym, eval_mode, init_mode):
+                     use_grad_scaling, grad_scaler, sym, eval_mode, init_mode, prologue=0, x2=None):
     _check_common(x, scale, shift)
     if scale.numel() < 1 or shift.numel() < 1:
         raise RuntimeError("scale and shift need at least one element")
     lib = _cabi.load()
     xd, _, _, n = _dense_layout(x)
+    x2p = _addend_ptr(x2, xd)
     y = torch.empty_like(xd)
     if n == 0:
         return y
     q = _qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
     with _on_device(x.device):
-        rc = lib.lsqb200_fwd_tensor(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), n,
-                                    _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
+        if prologue:
+            rc = lib.lsqb200_fwd_tensor_pre(xd.data_ptr(), x2p, y.data_ptr(), scale.data_ptr(), shift.data_ptr(), n,
+                                            _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, prologue, _stream_ptr(x.device))
+        else:
+            rc = lib.lsqb200_fwd_tensor(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), n,
+                                        _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
     _cabi.check(rc, "lsq_forward_per_tensor")
     return y
 
 
 def _bwd_tensor_cuda(grad, x, scale, shift, quant_min, quant_max, type_min, type_max,
-                     use_grad_scaling, grad_scaler, sym, eval_mode, init_mode):
+                     use_grad_scaling, grad_scaler, sym, eval_mode, init_mode, prologue=0, x2=None):
     _check_common(x, scale, shift)
     if grad.dtype != x.dtype:
         raise RuntimeError("`grad` and `input` must have the same floating-point type")
@@ -187,6 +208,7 @@ def _bwd_tensor_cuda(grad, x, scale, shift, quant_min, quant_max, type_min, type
         raise RuntimeError("`x` and `grad` are not the same size")
     lib = _cabi.load()
     xd, _, _, n = _dense_layout(x)
+    x2p = _addend_ptr(x2, xd)
     gd = _match_layout(grad, xd)
     gx = torch.empty_like(xd)
     gscale = torch.empty(1, dtype=scale.dtype, device=scale.device)
@@ -195,9 +217,14 @@ def _bwd_tensor_cuda(grad, x, scale, shift, quant_min, quant_max, type_min, type
     with _on_device(x.device):
         sp = _stream_ptr(x.device)
         ws = _workspace(x.device, sp)
-        rc = lib.lsqb200_bwd_tensor(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                    gscale.data_ptr(), gshift.data_ptr(), n, _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q,
-                                    ws.data_ptr(), ws.numel(), sp)
+        if prologue:
+            rc = lib.lsqb200_bwd_tensor_pre(gd.data_ptr(), xd.data_ptr(), x2p, gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                            gscale.data_ptr(), gshift.data_ptr(), n, _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q,
+                                            prologue, ws.data_ptr(), ws.numel(), sp)
+        else:
+            rc = lib.lsqb200_bwd_tensor(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                        gscale.data_ptr(), gshift.data_ptr(), n, _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q,
+                                        ws.data_ptr(), ws.numel(), sp)
     _cabi.check(rc, "lsq_backward_per_tensor")
     return gx, gscale, gshift
 
@@ -216,24 +243,29 @@ def _check_channel(x, scale, shift, axis):
 
 
 def _fwd_channel_cuda(x, scale, shift, axis, quant_min, quant_max, type_min, type_max,
-                      use_grad_scaling, grad_scaler, sym, eval_mode, init_mode):
+                      use_grad_scaling, grad_scaler, sym, eval_mode, init_mode, prologue=0, x2=None):
     _check_common(x, scale, shift)
     _check_channel(x, scale, shift, axis)
     lib = _cabi.load()
     xd, outer, C, inner = _dense_layout(x, axis)
+    x2p = _addend_ptr(x2, xd)
     y = torch.empty_like(xd)
     if x.numel() == 0:
         return y
     q = _qargs(quant_min, quant_max, type_min, type_max, use_grad_scaling, grad_scaler, sym, eval_mode, init_mode)
     with _on_device(x.device):
-        rc = lib.lsqb200_fwd_channel(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
-                                     _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
+        if prologue:
+            rc = lib.lsqb200_fwd_channel_pre(xd.data_ptr(), x2p, y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
+                                             _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, prologue, _stream_ptr(x.device))
+        else:
+            rc = lib.lsqb200_fwd_channel(xd.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
+                                         _DT_OPS[x.dtype], _DT_OPS[scale.dtype], q, _stream_ptr(x.device))
     _cabi.check(rc, "lsq_forward_per_channel")
     return y
 
 
 def _bwd_channel_cuda(grad, x, scale, shift, axis, quant_min, quant_max, type_min, type_max,
-                      use_grad_scaling, grad_scaler, sym, eval_mode, init_mode):
+                      use_grad_scaling, grad_scaler, sym, eval_mode, init_mode, prologue=0, x2=None):
     _check_common(x, scale, shift)
     _check_channel(x, scale, shift, axis)
     if grad.dtype != x.dtype:
@@ -242,6 +274,7 @@ def _bwd_channel_cuda(grad, x, scale, shift, axis, quant_min, quant_max, type_mi
         raise RuntimeError("`x` and `grad` are not the same size")
     lib = _cabi.load()
     xd, outer, C, inner = _dense_layout(x, axis)
+    x2p = _addend_ptr(x2, xd)
     gd = _match_layout(grad, xd)
     gx = torch.empty_like(xd)
     gscale = torch.empty(C, dtype=scale.dtype, device=scale.device)
@@ -250,9 +283,14 @@ def _bwd_channel_cuda(grad, x, scale, shift, axis, quant_min, quant_max, type_mi
     with _on_device(x.device):
         sp = _stream_ptr(x.device)
         ws = _workspace(x.device, sp)
-        rc = lib.lsqb200_bwd_channel(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
-                                     gscale.data_ptr(), gshift.data_ptr(), outer, C, inner, _DT_OPS[x.dtype],
-                                     _DT_OPS[scale.dtype], q, ws.data_ptr(), ws.numel(), sp)
+        if prologue:
+            rc = lib.lsqb200_bwd_channel_pre(gd.data_ptr(), xd.data_ptr(), x2p, gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                             gscale.data_ptr(), gshift.data_ptr(), outer, C, inner, _DT_OPS[x.dtype],
+                                             _DT_OPS[scale.dtype], q, prologue, ws.data_ptr(), ws.numel(), sp)
+        else:
+            rc = lib.lsqb200_bwd_channel(gd.data_ptr(), xd.data_ptr(), gx.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                         gscale.data_ptr(), gshift.data_ptr(), outer, C, inner, _DT_OPS[x.dtype],
+                                         _DT_OPS[scale.dtype], q, ws.data_ptr(), ws.numel(), sp)
     _cabi.check(rc, "lsq_backward_per_channel")
     return gx, gscale, gshift
 
@@ -378,6 +416,79 @@ def _lsq_front(x, scale, shift, quant_min, quant_max, type_min, type_max, axis, 
                                            use_grad_scaling, grad_scaler, not is_affine, eval_mode, init_mode)
     return torch.ops.torchlsq.lsq_forward_per_tensor(x, scale, shift, quant_min, quant_max, type_min, type_max,
                                                      use_grad_scaling, grad_scaler, not is_affine, eval_mode, init_mode)
+
+
+# ---- prologue fusion: fake_quant(relu(x)), fake_quant(relu(a + b)), fake_quant(a + b) in one pass; new
+#      surface, nothing in the reference to mirror -----------------------------------------------------------------------
+class _LSQPrePerTensorFunction(torch.autograd.Function):
+    """y = lsq(pre(x[, x2])); one backward pass gives grad_x (shared by both addends) and the parameter sums."""
+
+    @staticmethod
+    def forward(ctx, prologue, x, x2, scale, shift, *scalars):
+        out = _fwd_tensor_cuda(x, scale, shift, *scalars, prologue=prologue, x2=x2)
+        ctx.scalars, ctx.prologue, ctx.has_x2 = scalars, prologue, x2 is not None
+        ctx.save_for_backward(*((x, x2, scale, shift) if x2 is not None else (x, scale, shift)))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if torch.is_grad_enabled():
+            raise RuntimeError("double backwards on fused-prologue lsq not supported")
+        if ctx.has_x2:
+            x, x2, scale, shift = ctx.saved_tensors
+        else:
+            (x, scale, shift), x2 = ctx.saved_tensors, None
+        gx, gs, gb = _bwd_tensor_cuda(grad_output, x, scale, shift, *ctx.scalars, prologue=ctx.prologue, x2=x2)
+        return (None, gx, gx if ctx.has_x2 else None, gs, gb) + (None,) * 9
+
+
+class _LSQPrePerChannelFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prologue, x, x2, scale, shift, axis, *scalars):
+        out = _fwd_channel_cuda(x, scale, shift, axis, *scalars, prologue=prologue, x2=x2)
+        ctx.axis, ctx.scalars, ctx.prologue, ctx.has_x2 = axis, scalars, prologue, x2 is not None
+        ctx.save_for_backward(*((x, x2, scale, shift) if x2 is not None else (x, scale, shift)))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if torch.is_grad_enabled():
+            raise RuntimeError("double backwards on fused-prologue lsq not supported")
+        if ctx.has_x2:
+            x, x2, scale, shift = ctx.saved_tensors
+        else:
+            (x, scale, shift), x2 = ctx.saved_tensors, None
+        gx, gs, gb = _bwd_channel_cuda(grad_output, x, scale, shift, ctx.axis, *ctx.scalars, prologue=ctx.prologue, x2=x2)
+        return (None, gx, gx if ctx.has_x2 else None, gs, gb) + (None,) * 10
+
+
+def _lsq_pre_front(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max, axis, use_grad_scaling,
+                   grad_scaler, is_affine, is_perchannel, eval_mode, init_mode):
+    """Same checks and broadcast as `_lsq_front` (csrc/ops/lsq.cpp:104-134), prologue-fused kernels behind it."""
+    if scale.dim() != 1:
+        raise RuntimeError("scale should be a 1-D tensor, even in per tensor case(please, avoid torch.Scalar too)")
+    if shift.dim() != 1:
+        raise RuntimeError("shift should be a 1-D tensor, even in per tensor case(please, avoid torch.Scalar too)")
+    if not x.is_cuda:
+        raise RuntimeError("`input` tensor must be CUDA tensor (torchlsq-b200 has no CPU path)")
+    _check_prologue(x, scale)
+    if x2 is not None:
+        if x2.shape != x.shape or x2.dtype != x.dtype or x2.device != x.device:
+            raise RuntimeError("the two addends must have the same shape, dtype and device")
+        # both addends must share one dense layout: the first operand decides, the second is copied only if it differs
+        xd = _dense_layout(x, axis if is_perchannel else None)[0]
+        if xd.data_ptr() != x.data_ptr() or xd.stride() != x.stride():
+            x = xd
+        if x2.stride() != x.stride():
+            x2 = torch.empty_like(x).copy_(x2)
+    if is_perchannel:
+        size = max(scale.size(0), shift.size(0))
+        _scale = scale if size == scale.size(0) else scale.repeat(size)
+        _shift = shift if size == shift.size(0) else shift.repeat(size)
+        return _LSQPrePerChannelFunction.apply(prologue, x, x2, _scale, _shift, axis, quant_min, quant_max, type_min, type_max,
+                                               use_grad_scaling, grad_scaler, not is_affine, eval_mode, init_mode)
+    return _LSQPrePerTensorFunction.apply(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max,
+                                          use_grad_scaling, grad_scaler, not is_affine, eval_mode, init_mode)
 
 
 _TAIL = ("int quant_min, int quant_max, int type_min, int type_max, bool use_grad_scaling, float grad_scaler, "

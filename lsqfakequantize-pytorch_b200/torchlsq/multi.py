@@ -43,6 +43,8 @@ class Site:
     is_perchannel: bool = False
     eval_mode: bool = False
     init_mode: bool = False
+    fuse_relu: bool = False   # fake-quant of relu(x) in one pass (include/lsq_b200.h: LSQB200_PRE_RELU)
+    x2: Optional[torch.Tensor] = None   # second addend: the site quantises x + x2 (relu(x + x2) with fuse_relu), LSQB200_PRE_ADD*
 
 
 def _ptr(t):
@@ -68,9 +70,9 @@ class LSQPlan:
             xd, outer, C, inner = _dense_layout(s.x, s.axis if s.is_perchannel else None)
             if xd.data_ptr() != s.x.data_ptr():
                 raise RuntimeError("plan tensors must be dense (contiguous in some dimension order)")
-            for other in (s.y, s.grad, s.gx):
+            for other in (s.y, s.grad, s.gx, s.x2):
                 if other is not None and (other.shape != s.x.shape or other.stride() != s.x.stride() or other.dtype != s.x.dtype):
-                    raise RuntimeError("y / grad / gx must match x in shape, strides and dtype")
+                    raise RuntimeError("y / grad / gx / x2 must match x in shape, strides and dtype")
             nparam = C if s.is_perchannel else 1
             if s.scale.numel() != nparam or s.shift.numel() != nparam:
                 raise RuntimeError("scale / shift length does not match the channel count")
@@ -82,6 +84,11 @@ class LSQPlan:
             seg.outer, seg.C, seg.inner = outer, C, inner
             seg.xdtype, seg.pdtype = _DT[s.x.dtype], _DT[s.scale.dtype]
             seg.per_channel = int(s.is_perchannel)
+            if s.x2 is not None:
+                seg.prologue = _cabi.PRE_ADD_RELU if s.fuse_relu else _cabi.PRE_ADD
+                seg.x2 = _ptr(s.x2)
+            else:
+                seg.prologue = _cabi.PRE_RELU if s.fuse_relu else _cabi.PRE_NONE
             seg.q = _cabi.qargs(s.quant_min, s.quant_max, tmin, tmax, s.use_grad_scaling, s.grad_scaler,
                                 not s.is_affine, s.eval_mode, s.init_mode)
             nslots += nparam

@@ -25,7 +25,7 @@ from typing import Tuple
 import torch
 
 from ... import _cabi
-from ...functional import lsq
+from ...functional import lsq, lsq_relu
 
 Tensor = torch.Tensor
 
@@ -203,6 +203,10 @@ class LSQFakeQuantizer(ObserverBase):
         use_grad_scaling, grad_scaler: 1/sqrt(numel * quant_max) gradient scaling and an extra factor.
         avoid_torch_overflow: 7-bit default ranges.
         debug_mode: forward is the identity.
+        fuse_relu: (new, not in the reference) the module stands for `Sequential(ReLU(), LSQFakeQuantizer(...))`:
+            every value it returns or observes is taken from relu(x), and once the parameters are initialised the
+            ReLU runs inside the fake-quant kernels (`torchlsq.functional.lsq_relu`: one pass over x, forward and
+            backward) instead of as a separate pass.  Results are bit-identical to the two-module sequence.
     """
     init_modes = ('learnable', 'observer')
 
@@ -218,7 +222,7 @@ class LSQFakeQuantizer(ObserverBase):
                  ch_axis=None, learn_params=True,
                  init_batches=1000, init_mode='observer',
                  use_grad_scaling=True, grad_scaler=1.,
-                 avoid_torch_overflow=True, debug_mode=False, **observer_kwargs):
+                 avoid_torch_overflow=True, debug_mode=False, fuse_relu=False, **observer_kwargs):
         super().__init__(dtype)
         assert init_mode in self.init_modes, f'only following modes available: {self.init_modes}'
         self.activation_post_process = None
@@ -250,6 +254,7 @@ class LSQFakeQuantizer(ObserverBase):
         self.use_grad_scaling = use_grad_scaling
         self.grad_scaler = grad_scaler
         self.debug_mode = debug_mode
+        self.fuse_relu = bool(fuse_relu)
         self.is_perchannel = IS_QSCHEME_PER_CHANNEL(self.qscheme)
         self.is_affine = IS_QSCHEME_AFFINE(self.qscheme)
         self.init_scale = init_scale
@@ -410,9 +415,12 @@ class LSQFakeQuantizer(ObserverBase):
 
     # ------------------------------------------------------------------ forward
     def forward(self, x):
+        relu = self.fuse_relu                # True while relu(x) still has to be applied to what we return
         if self.debug_mode:
-            return x
+            return torch.relu(x) if relu else x
         if not self._initialized:
+            if relu:
+                x = torch.relu(x)
             self._init_weights(x)
             return x                     # the first call only creates the parameters
         backprop_init = False
@@ -431,6 +439,8 @@ class LSQFakeQuantizer(ObserverBase):
             self._m_batch += 1
 
         if self._m_obs == 1:
+            if relu:                     # the observer must see relu(x): materialise it while the range is being estimated
+                x, relu = torch.relu(x), False
             # fused native step for torch's MinMax-family observers; any other observer runs as in the reference
             if not (self.native_observer and observer_step(self.activation_post_process, x, self.scale.data, self.shift.data)):
                 self.activation_post_process(x.detach())
@@ -442,11 +452,17 @@ class LSQFakeQuantizer(ObserverBase):
             tmin, tmax = TYPES_RANGE_MAPPING[self.dtype]['range']
             self.scale.requires_grad = full_lsq
             self.shift.requires_grad = full_lsq and self.is_affine
-            return lsq(x, self.scale, self.shift, self.quant_min, self.quant_max, tmin, tmax,
+            op = lsq
+            if relu:
+                if x.is_cuda and x.dtype != torch.float64 and self.scale.dtype == torch.float32:
+                    op = lsq_relu        # steady state: ReLU inside the fake-quant kernels
+                else:
+                    x = torch.relu(x)
+            return op(x, self.scale, self.shift, self.quant_min, self.quant_max, tmin, tmax,
                        self.ch_axis, self.use_grad_scaling, self.grad_scaler,
                        self.is_affine, self.is_perchannel,
                        eval_mode=(not full_lsq), init_mode=bool(backprop_init))
-        return x
+        return torch.relu(x) if relu else x
 
     @torch.jit.export
     def extra_repr(self):

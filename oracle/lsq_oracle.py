@@ -159,6 +159,78 @@ def backward(g, x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=F
     return (gx, gs_, gb_, as_, ab_) if with_abs else (gx, gs_, gb_)
 
 
+# ---- prologue fusion: lsq(relu(x)) restated as the reference's own call sequence ---------------------------
+#      torch.relu (ATen clamp_min(x, 0): NaN stays NaN, negatives and -0 become +0) -> reference lsq op -> autograd through
+#      both (relu backward = threshold_backward: x <= 0 -> exact +0, otherwise the incoming gradient).  Pinned by
+#      tests/golden/ref_cpu_relu.npz (reference CPU op behind torch.relu, tests/golden/make_golden_relu.py).
+def _relu_masks(x, dt):
+    """(is_nan, nonpositive) of x given as fp32 / fp16 values or 16-bit patterns."""
+    xr = _raw(x)
+    if xr.dtype == np.uint16:
+        mag = xr & np.uint16(0x7FFF)
+        expo = np.uint16(0x7C00 if dt == F16 else 0x7F80)
+        nan = mag > expo
+        nonpos = ~nan & ((mag == 0) | ((xr >> 15) == 1))
+        return xr, nan, nonpos
+    nan = np.isnan(xr)
+    with np.errstate(invalid="ignore"):
+        nonpos = ~nan & (xr <= 0)
+    return xr, nan, nonpos
+
+
+def relu(x, dt=None, keep_neg_zero=False):
+    """torch.relu on values or 16-bit patterns; returns the same representation as `x`.
+    -0 input: ATen's CUDA kernel (fmaxf -> FMNMX, -0 < +0) and the sm_100a kernels return +0; ATen's CPU kernel
+    returns the -0 it was given (keep_neg_zero=True).  Only the learned-init forward (y = relu(x), a copy) can show
+    the difference; everything behind the fake-quant's fma(x, 1/s, zp) is blind to the sign of zero."""
+    dt = _dt_of(x, dt) if x.dtype != np.float64 else None
+    xr, _, nonpos = _relu_masks(x, dt)
+    out = xr.copy()
+    if keep_neg_zero:
+        nonpos = nonpos & ~((xr & np.uint16(0x7FFF)) == 0 if xr.dtype == np.uint16 else (xr == 0))
+    out[nonpos] = 0          # +0 in every representation
+    return out.view(x.dtype) if x.dtype == np.float16 else out
+
+
+def add(x, x2, dt=None):
+    """x + x2 as ATen's add stores it: fp32 sum, one rounding to the tensor type (values or 16-bit patterns in and out)."""
+    if x.dtype in (np.float32, np.float64):
+        with np.errstate(invalid="ignore", over="ignore"):
+            return (x + x2).astype(x.dtype)
+    dt = _dt_of(x, dt)
+    import torch
+    sh = np.shape(x)
+    out, _ = to_bits(from_bits(_raw(x).reshape(-1), dt) + from_bits(_raw(x2).reshape(-1), dt))
+    out = out.reshape(sh)
+    return out.view(np.float16) if x.dtype == np.float16 else out
+
+
+def forward_add(x, x2, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None, with_relu=True):
+    """lsq(relu(x + x2)) (with_relu) or lsq(x + x2): the reference op behind ATen's add [+ relu]."""
+    s = add(x, x2, dt)
+    return (forward_relu if with_relu else forward)(s, scale, shift, c, outer, C, inner, per_channel, dt)
+
+
+def backward_add(g, x, x2, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None, with_abs=False, with_relu=True):
+    """Backward of forward_add; the returned gx is the gradient of x and of x2 (add's backward passes it to both)."""
+    s = add(x, x2, dt)
+    return (backward_relu if with_relu else backward)(g, s, scale, shift, c, outer, C, inner, per_channel, dt, with_abs)
+
+
+def forward_relu(x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None):
+    return forward(relu(x, dt, keep_neg_zero=(c.contract == CONTRACT_CPU)), scale, shift, c, outer, C, inner, per_channel, dt)
+
+
+def backward_relu(g, x, scale, shift, c: Cfg, outer=1, C=1, inner=None, per_channel=False, dt=None, with_abs=False):
+    out = backward(g, relu(x, dt), scale, shift, c, outer, C, inner, per_channel, dt, with_abs)
+    dtc = _dt_of(x, dt) if x.dtype != np.float64 else None
+    _, _, nonpos = _relu_masks(x, dtc)
+    gx = _raw(out[0]).copy().reshape(-1)
+    gx[nonpos.reshape(-1)] = 0
+    gx = gx.view(x.dtype) if x.dtype == np.float16 else gx
+    return (gx,) + tuple(out[1:])
+
+
 def weight_init(w, quant_min, quant_max, outer=1, C=1, inner=None, dt=None):
     dt = _dt_of(w, dt)
     wr = _raw(w)

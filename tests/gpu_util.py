@@ -34,11 +34,19 @@ def ocfg(q, **kw):
     return O.cfg(**base)
 
 
-def fwd(x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False):
+def fwd(x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, prologue=0, x2=None):
     lib = _cabi.load()
     y = torch.empty_like(x)
     inner = x.numel() // (outer * C) if inner is None else inner
-    if per_channel:
+    x2p = None if x2 is None else x2.data_ptr()
+    if prologue:
+        if per_channel:
+            rc = lib.lsqb200_fwd_channel_pre(x.data_ptr(), x2p, y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
+                                             _DT[x.dtype], _DT[scale.dtype], q, prologue, stream())
+        else:
+            rc = lib.lsqb200_fwd_tensor_pre(x.data_ptr(), x2p, y.data_ptr(), scale.data_ptr(), shift.data_ptr(), x.numel(),
+                                            _DT[x.dtype], _DT[scale.dtype], q, prologue, stream())
+    elif per_channel:
         rc = lib.lsqb200_fwd_channel(x.data_ptr(), y.data_ptr(), scale.data_ptr(), shift.data_ptr(), outer, C, inner,
                                      _DT[x.dtype], _DT[scale.dtype], q, stream())
     else:
@@ -48,7 +56,7 @@ def fwd(x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False):
     return y
 
 
-def bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, want_gx=True):
+def bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, want_gx=True, prologue=0, x2=None):
     lib = _cabi.load()
     gx = torch.empty_like(x) if want_gx else None
     n = C if per_channel else 1
@@ -57,7 +65,17 @@ def bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, want
     ws = workspace()
     inner = x.numel() // (outer * C) if inner is None else inner
     gxp = gx.data_ptr() if want_gx else None
-    if per_channel:
+    x2p = None if x2 is None else x2.data_ptr()
+    if prologue:
+        if per_channel:
+            rc = lib.lsqb200_bwd_channel_pre(g.data_ptr(), x.data_ptr(), x2p, gxp, scale.data_ptr(), shift.data_ptr(),
+                                             gs.data_ptr(), gb.data_ptr(), outer, C, inner, _DT[x.dtype], _DT[scale.dtype], q,
+                                             prologue, ws.data_ptr(), ws.numel(), stream())
+        else:
+            rc = lib.lsqb200_bwd_tensor_pre(g.data_ptr(), x.data_ptr(), x2p, gxp, scale.data_ptr(), shift.data_ptr(),
+                                            gs.data_ptr(), gb.data_ptr(), x.numel(), _DT[x.dtype], _DT[scale.dtype], q,
+                                            prologue, ws.data_ptr(), ws.numel(), stream())
+    elif per_channel:
         rc = lib.lsqb200_bwd_channel(g.data_ptr(), x.data_ptr(), gxp, scale.data_ptr(), shift.data_ptr(),
                                      gs.data_ptr(), gb.data_ptr(), outer, C, inner, _DT[x.dtype], _DT[scale.dtype], q,
                                      ws.data_ptr(), ws.numel(), stream())
@@ -94,18 +112,25 @@ def count_diff(t: torch.Tensor, ref_np: np.ndarray):
     return int((a.reshape(-1).view(np.uint32) != b.view(np.uint32)).sum())
 
 
-def oracle_fwd(x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, **kw):
+def oracle_fwd(x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, relu=False, x2=None, **kw):
     xb, dt = O.to_bits(x)
     half_exact = (x.dtype == torch.float16 and scale.dtype == torch.float16)
-    return O.forward(xb.reshape(-1), scale.float().cpu().numpy(), shift.float().cpu().numpy(),
+    if x2 is not None:
+        return O.forward_add(xb.reshape(-1), O.to_bits(x2)[0].reshape(-1), scale.float().cpu().numpy(), shift.float().cpu().numpy(),
+                             ocfg(q, **kw), outer, C, inner, per_channel, dt=dt, with_relu=relu)
+    return (O.forward_relu if relu else O.forward)(xb.reshape(-1), scale.float().cpu().numpy(), shift.float().cpu().numpy(),
                      ocfg(q, half_exact=half_exact, **kw), outer, C, inner, per_channel, dt=dt)
 
 
-def oracle_bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, **kw):
+def oracle_bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=False, relu=False, x2=None, **kw):
     xb, dt = O.to_bits(x)
     gb, _ = O.to_bits(g)
     half_exact = (x.dtype == torch.float16 and scale.dtype == torch.float16)
-    return O.backward(gb.reshape(-1), xb.reshape(-1), scale.float().cpu().numpy(), shift.float().cpu().numpy(),
+    if x2 is not None:
+        return O.backward_add(gb.reshape(-1), xb.reshape(-1), O.to_bits(x2)[0].reshape(-1), scale.float().cpu().numpy(),
+                              shift.float().cpu().numpy(), ocfg(q, **kw), outer, C, inner, per_channel, dt=dt, with_abs=True,
+                              with_relu=relu)
+    return (O.backward_relu if relu else O.backward)(gb.reshape(-1), xb.reshape(-1), scale.float().cpu().numpy(), shift.float().cpu().numpy(),
                       ocfg(q, half_exact=half_exact, **kw), outer, C, inner, per_channel, dt=dt, with_abs=True)
 
 
