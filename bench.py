@@ -402,6 +402,15 @@ def run_b200(args):
                      "note": "torchlsq.multi.LSQPlan: all 71 activation sites in one launch per direction"}
         p2.close()
 
+    # ---- prologue fusion at workload level: the same 71 + 54 sites, but 33 sites sit behind a ReLU and 16 behind
+    #      a residual add + ReLU (torchvision resnet50: conv1 + 2 per block; 1 per block).  "unfused" runs those ops as the
+    #      network does today - ATen add / relu passes in front of the plain kernels, threshold_backward behind them -,
+    #      "fused" runs them inside the fake-quant kernels (lsqb200_*_pre).  Same results bit for bit (tests/test_gpu_relu.py,
+    #      tests/test_gpu_add.py); the figure is ms per step over ALL sites, N = 1 only.
+    fusion_mode = None
+    if world == 1 and not args.no_fusion_mode:
+        fusion_mode = run_fusion_mode(args, torch, lib, acts, flat, ws, sp, stream, wplan, qa, BF16, F32, dev, gen)
+
     # ---- mu +- 3 sigma init throughput (one launch over all 54 weights)
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(3):
@@ -461,7 +470,7 @@ def run_b200(args):
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": bwd_bytes, "avg_ms_per_step": round(bwd_ms, 4)},
-            "plan_mode": plan_mode, "weight_init_stats_GBps": round(init_gbps, 1), "dp_check": dp_check,
+            "plan_mode": plan_mode, "prologue_fusion": fusion_mode, "weight_init_stats_GBps": round(init_gbps, 1), "dp_check": dp_check,
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(),
         }
@@ -470,6 +479,84 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+# per-image shapes of the sites that sit behind a ReLU / behind the residual add + ReLU of a block (torchvision resnet50)
+RELU_SITES = {(64, 112, 112): 1, (64, 56, 56): 6, (128, 56, 56): 1, (128, 28, 28): 7, (256, 28, 28): 1, (256, 14, 14): 11,
+              (512, 14, 14): 1, (512, 7, 7): 5}
+JOIN_SITES = {(256, 56, 56): 3, (512, 28, 28): 4, (1024, 14, 14): 6, (2048, 7, 7): 3}
+
+
+def run_fusion_mode(args, torch, lib, acts, flat, ws, sp, stream, wplan, qa, BF16, F32, dev, gen):
+    relu_left, join_left = dict(RELU_SITES), dict(JOIN_SITES)
+    kinds = []
+    for a, shp in zip(acts, ACT_SHAPES):
+        if relu_left.get(shp, 0) > 0:
+            relu_left[shp] -= 1
+            kinds.append("relu")
+        elif join_left.get(shp, 0) > 0:
+            join_left[shp] -= 1
+            kinds.append("join")
+        else:
+            kinds.append("plain")
+    assert kinds.count("relu") == 33 and kinds.count("join") == 16
+    fused_f, fused_b, unf_f, unf_b = [], [], [], []
+    for a, kind in zip(acts, kinds):
+        gs, gb = flat.views(a["name"])
+        x, y, g, gx, s, b, n = a["x"], a["y"], a["g"], a["gx"], a["s"], a["b"], a["n"]
+        plain_f = (lib.lsqb200_fwd_tensor, (x.data_ptr(), y.data_ptr(), s.data_ptr(), b.data_ptr(), n, BF16, F32, qa, sp))
+        plain_b = (lib.lsqb200_bwd_tensor, (g.data_ptr(), x.data_ptr(), gx.data_ptr(), s.data_ptr(), b.data_ptr(), gs.data_ptr(),
+                                            gb.data_ptr(), n, BF16, F32, qa, ws.data_ptr(), ws.numel(), sp))
+        if kind == "plain":
+            fused_f.append(plain_f); fused_b.append(plain_b); unf_f.append(plain_f); unf_b.append(plain_b)
+            continue
+        # pre-activation input(s): zero-mean so that the ReLU has work to do; t = the activation tensor the unfused network holds
+        pre = torch.empty(n, dtype=torch.bfloat16, device=dev).normal_(0, 1, generator=gen)
+        t, gt = torch.empty_like(pre), torch.empty_like(pre)
+        pre2 = torch.empty(n, dtype=torch.bfloat16, device=dev).normal_(0, 1, generator=gen) if kind == "join" else None
+        code = 2 if kind == "join" else 1
+        p2 = pre2.data_ptr() if pre2 is not None else None
+        fused_f.append((lib.lsqb200_fwd_tensor_pre, (pre.data_ptr(), p2, y.data_ptr(), s.data_ptr(), b.data_ptr(), n, BF16, F32, qa, code, sp)))
+        fused_b.append((lib.lsqb200_bwd_tensor_pre, (g.data_ptr(), pre.data_ptr(), p2, gx.data_ptr(), s.data_ptr(), b.data_ptr(),
+                                                     gs.data_ptr(), gb.data_ptr(), n, BF16, F32, qa, code, ws.data_ptr(), ws.numel(), sp)))
+        if kind == "join":      # torchvision: out += identity; out = relu_(out)
+            unf_f.append((lambda pre=pre, pre2=pre2, t=t: (torch.add(pre, pre2, out=t), t.relu_()), ()))
+        else:                   # relu (out of place so that the step is repeatable; same traffic as relu_: R + W)
+            unf_f.append((lambda pre=pre, t=t: torch.clamp_min(pre, 0, out=t), ()))
+        unf_f.append((lib.lsqb200_fwd_tensor, (t.data_ptr(), y.data_ptr(), s.data_ptr(), b.data_ptr(), n, BF16, F32, qa, sp)))
+        unf_b.append((lib.lsqb200_bwd_tensor, (g.data_ptr(), t.data_ptr(), gx.data_ptr(), s.data_ptr(), b.data_ptr(), gs.data_ptr(),
+                                               gb.data_ptr(), n, BF16, F32, qa, ws.data_ptr(), ws.numel(), sp)))
+        unf_b.append((lambda gx=gx, t=t, gt=gt: torch.ops.aten.threshold_backward(gx, t, 0, grad_input=gt), ()))
+    fused_b.reverse(); unf_b.reverse()
+
+    def run(fcalls, bcalls):
+        for fn, a_ in fcalls:
+            fn(*a_)
+        wplan.forward()
+        for fn, a_ in bcalls:
+            fn(*a_)
+        wplan.backward()
+
+    out = {}
+    for name, fc, bc in (("unfused", unf_f, unf_b), ("fused", fused_f, fused_b)):
+        for _ in range(3):
+            run(fc, bc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            run(fc, bc)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / args.steps
+    n_relu = sum(a["n"] for a, k in zip(acts, kinds) if k == "relu")
+    n_join = sum(a["n"] for a, k in zip(acts, kinds) if k == "join")
+    return {"unfused_ms_per_step": round(out["unfused"], 4), "fused_ms_per_step": round(out["fused"], 4),
+            "speedup": round(out["unfused"] / out["fused"], 3),
+            "sites": {"relu_then_fq": 33, "add_relu_then_fq": 16, "plain": 22, "weights": 54},
+            "hbm_bytes_removed_per_step": 2 * (5 * n_relu + 6 * n_join),
+            "note": "all 71 + 54 sites fwd+bwd; unfused = ATen clamp_min / add + relu_ / threshold_backward passes around the plain "
+                    "kernels (as torchvision's resnet50 runs them), fused = lsqb200_*_pre with LSQB200_PRE_RELU / PRE_ADD_RELU"}
 
 
 def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
@@ -591,6 +678,7 @@ def main():
     ap.add_argument("--no-plan-mode", action="store_true", help="skip the extra multi-tensor-plan measurement")
     ap.add_argument("--plan-activations", action="store_true", help="run all activation sites through one multi-tensor plan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fusion-mode", action="store_true", help="skip the workload-level prologue-fusion measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
