@@ -25,7 +25,7 @@ from typing import Tuple
 import torch
 
 from ... import _cabi
-from ...functional import lsq, lsq_relu
+from ...functional import lsq, lsq_add, lsq_add_relu, lsq_relu
 
 Tensor = torch.Tensor
 
@@ -415,12 +415,29 @@ class LSQFakeQuantizer(ObserverBase):
 
     # ------------------------------------------------------------------ forward
     def forward(self, x):
-        relu = self.fuse_relu                # True while relu(x) still has to be applied to what we return
+        return self._run(x, None, self.fuse_relu)
+
+    def forward_add(self, a, b, relu=True):
+        """(new, not in the reference) The module applied to `relu(a + b)` (or `a + b`): what
+        `FloatFunctional.add_relu` / `.add` do with this module as their `activation_post_process` - residual join,
+        activation and fake-quant in one kernel pass once the parameters are initialised (`torchlsq.functional.lsq_add_relu`).
+        Same state machine and bit-identical results as `self(torch.relu(a + b))`."""
+        return self._run(a, b, bool(relu))
+
+    def _run(self, x, x2, relu):
+        # `pending`: the prologue (residual add and / or ReLU) still has to be applied to whatever we return or observe
+        pending = relu or x2 is not None
+
+        def materialise(t):
+            if x2 is not None:
+                t = t + x2
+            return torch.relu(t) if relu else t
+
         if self.debug_mode:
-            return torch.relu(x) if relu else x
+            return materialise(x) if pending else x
         if not self._initialized:
-            if relu:
-                x = torch.relu(x)
+            if pending:
+                x = materialise(x)
             self._init_weights(x)
             return x                     # the first call only creates the parameters
         backprop_init = False
@@ -439,8 +456,8 @@ class LSQFakeQuantizer(ObserverBase):
             self._m_batch += 1
 
         if self._m_obs == 1:
-            if relu:                     # the observer must see relu(x): materialise it while the range is being estimated
-                x, relu = torch.relu(x), False
+            if pending:                  # the observer must see the site's real input: materialise it while the range is being estimated
+                x, pending = materialise(x), False
             # fused native step for torch's MinMax-family observers; any other observer runs as in the reference
             if not (self.native_observer and observer_step(self.activation_post_process, x, self.scale.data, self.shift.data)):
                 self.activation_post_process(x.detach())
@@ -452,17 +469,17 @@ class LSQFakeQuantizer(ObserverBase):
             tmin, tmax = TYPES_RANGE_MAPPING[self.dtype]['range']
             self.scale.requires_grad = full_lsq
             self.shift.requires_grad = full_lsq and self.is_affine
-            op = lsq
-            if relu:
+            tail = (self.scale, self.shift, self.quant_min, self.quant_max, tmin, tmax,
+                    self.ch_axis, self.use_grad_scaling, self.grad_scaler, self.is_affine, self.is_perchannel)
+            if pending:
                 if x.is_cuda and x.dtype != torch.float64 and self.scale.dtype == torch.float32:
-                    op = lsq_relu        # steady state: ReLU inside the fake-quant kernels
-                else:
-                    x = torch.relu(x)
-            return op(x, self.scale, self.shift, self.quant_min, self.quant_max, tmin, tmax,
-                       self.ch_axis, self.use_grad_scaling, self.grad_scaler,
-                       self.is_affine, self.is_perchannel,
-                       eval_mode=(not full_lsq), init_mode=bool(backprop_init))
-        return torch.relu(x) if relu else x
+                    # steady state: the prologue runs inside the fake-quant kernels
+                    if x2 is None:
+                        return lsq_relu(x, *tail, eval_mode=(not full_lsq), init_mode=bool(backprop_init))
+                    return (lsq_add_relu if relu else lsq_add)(x, x2, *tail, eval_mode=(not full_lsq), init_mode=bool(backprop_init))
+                x = materialise(x)
+            return lsq(x, *tail, eval_mode=(not full_lsq), init_mode=bool(backprop_init))
+        return materialise(x) if pending else x
 
     @torch.jit.export
     def extra_repr(self):
