@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LSQB200_ABI_VERSION 1
+#define LSQB200_ABI_VERSION 2   /* 2: lsqb200_segment gained `prologue` (was reserved) and a trailing `x2`; lsqb200_*_pre entry points */
 
 #if defined(__GNUC__)
 #define LSQB200_API __attribute__((visibility("default")))

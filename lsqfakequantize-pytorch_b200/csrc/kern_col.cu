@@ -68,14 +68,19 @@ ColKernelFn get_col_bwd_tma_kernel(int xdtype, int mode, int bmode, int tv, int*
 }
 ColKernelFn get_col_fwd_kernel(int xdtype, int mode, bool init, int v) {
     if (mode == M_FP32_RELU) return get_col_fwd_kernel_pre_relu(xdtype, init);
+    if (mode == M_FP32_ADD_RELU) return get_col_fwd_kernel_pre_addrelu(xdtype, init);
+    if (mode == M_FP32_ADD) return get_col_fwd_kernel_pre_add(xdtype, init);
     if (xdtype == DT_F32) return pick_f<float, M_FP32>(init, v);
     if (xdtype == DT_BF16) return pick_f<__nv_bfloat16, M_FP32>(init, v);
     return mode == M_HALF_EXACT ? pick_f<__half, M_HALF_EXACT>(init, v) : pick_f<__half, M_FP32>(init, v);
 }
 ColKernelFn get_col_bwd_kernel(int xdtype, int mode, int bmode, int v) {
-    if (mode == M_FP32_RELU)
-        return xdtype == DT_F32 ? get_col_bwd_kernel_pre_relu_f32(bmode)
-                                : (xdtype == DT_F16 ? get_col_bwd_kernel_pre_relu_f16(bmode) : get_col_bwd_kernel_pre_relu_bf16(bmode));
+#define LSQ_PICK_COL(P) (xdtype == DT_F32 ? get_col_bwd_kernel_pre_##P##_f32(bmode) \
+                         : (xdtype == DT_F16 ? get_col_bwd_kernel_pre_##P##_f16(bmode) : get_col_bwd_kernel_pre_##P##_bf16(bmode)))
+    if (mode == M_FP32_RELU) return LSQ_PICK_COL(relu);
+    if (mode == M_FP32_ADD_RELU) return LSQ_PICK_COL(addrelu);
+    if (mode == M_FP32_ADD) return LSQ_PICK_COL(add);
+#undef LSQ_PICK_COL
     if (xdtype == DT_F32) return pick_b<float, M_FP32>(bmode, v);
     if (xdtype == DT_BF16) return pick_b<__nv_bfloat16, M_FP32>(bmode, v);
     return mode == M_HALF_EXACT ? pick_b<__half, M_HALF_EXACT>(bmode, v) : pick_b<__half, M_FP32>(bmode, v);

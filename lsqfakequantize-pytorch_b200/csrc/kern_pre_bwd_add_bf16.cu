@@ -3,5 +3,5 @@
 #define LSQ_PRE_T __nv_bfloat16
 #define LSQ_PRE_SUFFIX add_bf16
 #define LSQ_PRE_MINB kMinBlocksBwdAdd
-
+#define LSQ_PRE_COLUMN 1
 #include "kern_pre_bwd.inc"

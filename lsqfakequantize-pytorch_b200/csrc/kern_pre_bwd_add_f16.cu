@@ -3,5 +3,5 @@
 #define LSQ_PRE_T __half
 #define LSQ_PRE_SUFFIX add_f16
 #define LSQ_PRE_MINB kMinBlocksBwdAdd
-
+#define LSQ_PRE_COLUMN 1
 #include "kern_pre_bwd.inc"

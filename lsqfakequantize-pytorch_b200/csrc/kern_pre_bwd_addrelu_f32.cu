@@ -3,5 +3,5 @@
 #define LSQ_PRE_T float
 #define LSQ_PRE_SUFFIX addrelu_f32
 #define LSQ_PRE_MINB kMinBlocksBwdAdd
-
+#define LSQ_PRE_COLUMN 1
 #include "kern_pre_bwd.inc"

@@ -2,5 +2,5 @@
 #define LSQ_PRE_MODE M_FP32_ADD
 #define LSQ_PRE_SUFFIX add
 #define LSQ_PRE_MINB kMinBlocksFwdAdd
-
+#define LSQ_PRE_COLUMN 1
 #include "kern_pre_fwd.inc"

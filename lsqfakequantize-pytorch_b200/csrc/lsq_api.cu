@@ -164,11 +164,11 @@ ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_
     return g;
 }
 
-ColSeg make_colseg(const ColGeom& g, const void* x, void* y, const void* grad, void* gx, const void* scale, const void* shift,
+ColSeg make_colseg(const ColGeom& g, const void* x, const void* x2, void* y, const void* grad, void* gx, const void* scale, const void* shift,
                    void* gscale, void* gshift, int64_t outer, int64_t C, int64_t inner, int pdt, const lsqb200_qargs* q,
                    void* workspace) {
     ColSeg cs{};
-    cs.x = x; cs.y = y; cs.g = grad; cs.gx = gx; cs.scale = scale; cs.shift = shift; cs.gscale = gscale; cs.gshift = gshift;
+    cs.x = x; cs.x2 = x2; cs.y = y; cs.g = grad; cs.gx = gx; cs.scale = scale; cs.shift = shift; cs.gscale = gscale; cs.gshift = gshift;
     if (workspace) {
         cs.counter = reinterpret_cast<unsigned*>(workspace);
         cs.acc = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + kColAccOffset);
@@ -221,11 +221,11 @@ int forward_common(const void* x, const void* x2, void* y, const void* scale, co
     if (outer * C * inner == 0) return 0;
     if (!x || !y || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
     if (xdt == DT_F64 && common_alignment({x, y, scale, shift}) < 8) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
-    if (per_channel && xdt != DT_F64 && !mode_add(mode)) {
+    if (per_channel && xdt != DT_F64) {
         ColKernelFn ck = get_col_fwd_kernel(xdt, mode, q->init_mode != 0, tuning().col_variant);
-        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, y}), tuning(), occupancy_of((const void*)ck, kColThreads), false, mode_relu(mode));
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, x2, y}), tuning(), occupancy_of((const void*)ck, kColThreads), false, mode_relu(mode) || mode_add(mode));
         if (cg.ok) {
-            const ColSeg cs = make_colseg(cg, x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, pdt, q, nullptr);
+            const ColSeg cs = make_colseg(cg, x, x2, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, pdt, q, nullptr);
             return launch_col(ck, cs, cg, (cudaStream_t)stream);
         }
     }
@@ -262,14 +262,14 @@ int backward_common(const void* grad, const void* x, const void* x2, void* gx, c
     if (!grad || !x || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
     if (xdt == DT_F64 && common_alignment({x, grad, gx, scale, shift, gscale, gshift}) < 8)
         return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
-    if (per_channel && xdt != DT_F64 && !mode_add(mode)) {
+    if (per_channel && xdt != DT_F64) {
         ColKernelFn ck = get_col_bwd_kernel(xdt, mode, bmode_of(q), tuning().col_variant);
-        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads), true, mode_relu(mode));
+        const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, x2, grad, gx}), tuning(), occupancy_of((const void*)ck, kColThreads), true, mode_relu(mode) || mode_add(mode));
         if (cg.ok) {
             if (!workspace || wbytes < kWorkspaceBytes || (reinterpret_cast<uintptr_t>(workspace) & 15u) != 0)
                 return fail(LSQB200_ERR_WORKSPACE, "workspace missing, misaligned or smaller than lsqb200_workspace_bytes()");
             const long long upr16 = C * inner * elem_size(xdt) / 16;
-            if (tuning().col_tma > 0 && upr16 >= kTmaConsumers && !mode_relu(mode)) {
+            if (tuning().col_tma > 0 && upr16 >= kTmaConsumers && !mode_relu(mode) && !mode_add(mode)) {
                 // TMA-staged variant: a CTA owns 256 column units (4 KB of every row) and a contiguous run of rows
                 int smem = 0;
                 ColKernelFn tk = get_col_bwd_tma_kernel(xdt, mode, bmode_of(q), tuning().col_tma, &smem);
@@ -284,10 +284,10 @@ int backward_common(const void* grad, const void* x, const void* x2, void* gx, c
                 tg.rows_per_split = rows;
                 tg.row_splits = (outer + rows - 1) / rows;
                 if (tg.row_splits > 65535) { tg.rows_per_split = (outer + 65534) / 65535; tg.row_splits = (outer + tg.rows_per_split - 1) / tg.rows_per_split; }
-                const ColSeg cs = make_colseg(tg, x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, pdt, q, workspace);
+                const ColSeg cs = make_colseg(tg, x, nullptr, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, pdt, q, workspace);
                 return launch_col(tk, cs, tg, st, kTmaThreads, smem);
             }
-            const ColSeg cs = make_colseg(cg, x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, pdt, q, workspace);
+            const ColSeg cs = make_colseg(cg, x, x2, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, pdt, q, workspace);
             return launch_col(ck, cs, cg, st);
         }
     }

@@ -20,6 +20,7 @@ namespace lsqb200 {
 
 struct ColSeg {
     const void* x;
+    const void* x2;       // second addend (ADD prologues), same layout as x
     void* y;
     const void* g;
     void* gx;
@@ -97,7 +98,8 @@ template <typename T, int MODE, bool INIT, int CNW, int kColUnroll, int MINB, in
 __global__ void __launch_bounds__(kColThreads, MINB)
 lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
     constexpr int NW = CNW, VEC = ColVec<T, CNW>::VEC, UB = CNW * 4;
-    constexpr bool RAWCOPY = INIT && !mode_relu(MODE);
+    constexpr bool RAWCOPY = INIT && !mode_relu(MODE) && !mode_add(MODE);
+    constexpr bool ADD = mode_add(MODE);
     asm volatile("griddepcontrol.launch_dependents;");
     const int tx = threadIdx.x % cs.tx, ty = threadIdx.x / cs.tx;
     const long long uc = (long long)blockIdx.x * cs.tx + tx;
@@ -105,6 +107,7 @@ lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
     ColWalk w;
     w.init(cs, uc, ty, UB);
     const char* __restrict__ px = reinterpret_cast<const char*>(cs.x) + w.off;
+    const char* __restrict__ px2 = ADD ? reinterpret_cast<const char*>(cs.x2) + w.off : nullptr;
     char* __restrict__ py = reinterpret_cast<char*>(cs.y) + w.off;
     asm volatile("griddepcontrol.wait;" ::: "memory");
     SlotParams<T, MODE, CNW> sp;
@@ -112,19 +115,29 @@ lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
     int cnt = w.cnt;
     // whole groups of kColUnroll rows: unconditional loads and stores
     for (; cnt >= kColUnroll; cnt -= kColUnroll) {
-        Raw<NW> xr[kColUnroll];
+        Raw<NW> xr[kColUnroll], x2r[ADD ? kColUnroll : 1];
 #pragma unroll
-        for (int r = 0; r < kColUnroll; r++) xr[r] = ld_unit<LD, NW>(px + r * w.stride);
+        for (int r = 0; r < kColUnroll; r++) {
+            xr[r] = ld_unit<LD, NW>(px + r * w.stride);
+            if constexpr (ADD) x2r[r] = ld_unit<LD, NW>(px2 + r * w.stride);
+        }
 #pragma unroll
         for (int r = 0; r < kColUnroll; r++) {
             if (RAWCOPY) { st_unit<ST, NW>(py + r * w.stride, xr[r]); continue; }
             float f[VEC];
             unpack_unit<T, NW>(xr[r], f);
+            if constexpr (ADD) {
+                float f2[VEC];
+                unpack_unit<T, NW>(x2r[r], f2);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) f[k] = pre_add<T>(f[k], f2[k]);
+            }
 #pragma unroll
             for (int k = 0; k < VEC; k++) f[k] = INIT ? pre_op<MODE>(f[k]) : fq_forward<MODE>(f[k], sp.chan(k, cs));
             st_unit<ST, NW>(py + r * w.stride, pack_unit<T, NW>(f));
         }
         px += kColUnroll * w.stride; py += kColUnroll * w.stride;
+        if constexpr (ADD) px2 += kColUnroll * w.stride;
     }
     for (; cnt > 0; cnt--) {
         const Raw<NW> xr = ld_unit<LD, NW>(px);
@@ -132,6 +145,13 @@ lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
         else {
             float f[VEC];
             unpack_unit<T, NW>(xr, f);
+            if constexpr (ADD) {
+                float f2[VEC];
+                unpack_unit<T, NW>(ld_unit<LD, NW>(px2), f2);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) f[k] = pre_add<T>(f[k], f2[k]);
+                px2 += w.stride;
+            }
 #pragma unroll
             for (int k = 0; k < VEC; k++) f[k] = INIT ? pre_op<MODE>(f[k]) : fq_forward<MODE>(f[k], sp.chan(k, cs));
             st_unit<ST, NW>(py, pack_unit<T, NW>(f));
@@ -147,6 +167,7 @@ __global__ void __launch_bounds__(kColThreads, MINB)
 lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
     constexpr int NW = CNW, VEC = ColVec<T, CNW>::VEC, UB = CNW * 4;
     constexpr int FLUSH_ROWS = 32;                            // promote fp32 partials to fp64 every 32 rows
+    constexpr bool ADD = mode_add(MODE);
     // private fp64 accumulators of every thread's element slots, [S|B][slot][thread]: no atomics, no conflicts
     __shared__ double sacc[2][VEC][kColThreads];
     __shared__ int last_flag;
@@ -163,6 +184,7 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
         w.init(cs, uc, ty, UB);
         const char* __restrict__ px = reinterpret_cast<const char*>(cs.x) + w.off;
         const char* __restrict__ pg = reinterpret_cast<const char*>(cs.g) + w.off;
+        const char* __restrict__ px2 = ADD ? reinterpret_cast<const char*>(cs.x2) + w.off : nullptr;
         char* __restrict__ pgx = cs.gx ? reinterpret_cast<char*>(cs.gx) + w.off : nullptr;
         SlotParams<T, MODE, CNW> sp;
         sp.load(cs, uc);
@@ -173,9 +195,15 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
                 sacc[1][k][threadIdx.x] += (double)accB[k]; accB[k] = 0.f;
             }
         };
-        auto row = [&](const Raw<NW>& xr, const Raw<NW>& gr, char* dst) {
+        auto row = [&](const Raw<NW>& xr, const Raw<NW>& x2r, const Raw<NW>& gr, char* dst) {
             float fx[VEC], fg[VEC];
             unpack_unit<T, NW>(xr, fx);
+            if constexpr (ADD) {
+                float f2[VEC];
+                unpack_unit<T, NW>(x2r, f2);
+#pragma unroll
+                for (int k = 0; k < VEC; k++) fx[k] = pre_add<T>(fx[k], f2[k]);
+            }
             unpack_unit<T, NW>(gr, fg);
 #pragma unroll
             for (int k = 0; k < VEC; k++)
@@ -187,21 +215,25 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
         };
         int cnt = w.cnt, since = 0;
         for (; cnt >= kColUnroll; cnt -= kColUnroll) {
-            Raw<NW> xr[kColUnroll], gr[kColUnroll];
+            Raw<NW> xr[kColUnroll], gr[kColUnroll], x2r[ADD ? kColUnroll : 1];
 #pragma unroll
             for (int r = 0; r < kColUnroll; r++) {
                 xr[r] = ld_unit<LD, NW>(px + r * w.stride);
+                if constexpr (ADD) x2r[r] = ld_unit<LD, NW>(px2 + r * w.stride);
                 gr[r] = ld_unit<LD, NW>(pg + r * w.stride);
             }
 #pragma unroll
-            for (int r = 0; r < kColUnroll; r++) row(xr[r], gr[r], pgx ? pgx + r * w.stride : nullptr);
+            for (int r = 0; r < kColUnroll; r++) row(xr[r], x2r[ADD ? r : 0], gr[r], pgx ? pgx + r * w.stride : nullptr);
             px += kColUnroll * w.stride; pg += kColUnroll * w.stride;
+            if constexpr (ADD) px2 += kColUnroll * w.stride;
             if (pgx) pgx += kColUnroll * w.stride;
             if (bmode_reduces(BMODE) && (since += kColUnroll) >= FLUSH_ROWS) { since = 0; flush(); }
         }
         for (; cnt > 0; cnt--) {
             const Raw<NW> xr = ld_unit<LD, NW>(px), gr = ld_unit<LD, NW>(pg);
-            row(xr, gr, pgx);
+            Raw<NW> x2r;
+            if constexpr (ADD) { x2r = ld_unit<LD, NW>(px2); px2 += w.stride; } else x2r = xr;
+            row(xr, x2r, gr, pgx);
             px += w.stride; pg += w.stride;
             if (pgx) pgx += w.stride;
         }
@@ -446,12 +478,16 @@ ColKernelFn get_col_fwd_kernel(int xdtype, int mode, bool init, int variant);
 ColKernelFn get_col_bwd_kernel(int xdtype, int mode, int bmode, int variant);
 // TMA-staged backward: tma_variant 1 = (R 4 rows, S 3 stages, 96 KB ring), 2 = (2, 4, 64 KB), 3 = (8, 3, 192 KB); sets *smem_bytes
 ColKernelFn get_col_bwd_tma_kernel(int xdtype, int mode, int bmode, int tma_variant, int* smem_bytes);
-// kern_pre_*_relu*.cu: MODE = M_FP32_RELU, default variant only (the variant knob is an experiment switch of the plain
-// kernels).  The two-operand ADD prologues have no column-layout kernels: short channel rows take the row-tiled path.
-ColKernelFn get_col_fwd_kernel_pre_relu(int xdtype, bool init);
-ColKernelFn get_col_bwd_kernel_pre_relu_f32(int bmode);
-ColKernelFn get_col_bwd_kernel_pre_relu_f16(int bmode);
-ColKernelFn get_col_bwd_kernel_pre_relu_bf16(int bmode);
+// kern_pre_*.cu: fused prologues, default variant only (the variant knob is an experiment switch of the plain kernels)
+#define LSQ_DECL_PRE_COL(P)                                      \
+    ColKernelFn get_col_fwd_kernel_pre_##P(int xdtype, bool init); \
+    ColKernelFn get_col_bwd_kernel_pre_##P##_f32(int bmode);       \
+    ColKernelFn get_col_bwd_kernel_pre_##P##_f16(int bmode);       \
+    ColKernelFn get_col_bwd_kernel_pre_##P##_bf16(int bmode);
+LSQ_DECL_PRE_COL(relu)
+LSQ_DECL_PRE_COL(addrelu)
+LSQ_DECL_PRE_COL(add)
+#undef LSQ_DECL_PRE_COL
 constexpr int kColVariantRelu = 1;
 // variant -> (unit words, rows in flight, min CTAs/SM); index with Tuning::col_variant
 constexpr int kColVariants = 6;

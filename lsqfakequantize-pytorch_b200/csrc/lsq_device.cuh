@@ -604,8 +604,7 @@ __device__ __forceinline__ bool channel_finish(const Seg& sg, const TileCtx& tl,
     group_sum2<G, THREADS>(a, b, red);
     if (sg.splits == 1) return true;
     if (tg == 0) {
-        sg.partials[2 * tl.ltile] = a;
-        sg.partials[2 * tl.ltile + 1] = b;
+        reinterpret_cast<double2*>(sg.partials)[tl.ltile] = make_double2(a, b);
         __threadfence();
         const unsigned prev = atomicAdd(&sg.counters[tl.c], 1u);
         *last_flag = (prev == (unsigned)sg.splits - 1u);
@@ -615,8 +614,20 @@ __device__ __forceinline__ bool channel_finish(const Seg& sg, const TileCtx& tl,
     if (!last) return false;
     __threadfence();
     a = 0.0; b = 0.0;
-    const double* p = sg.partials + 2 * (tl.c * sg.splits);
-    for (int i = tg; i < sg.splits; i += G) { a += __ldcg(p + 2 * i); b += __ldcg(p + 2 * i + 1); }
+    // every thread first ISSUES all of its partial-pair loads (one 128-bit L2 read each, four per round: a single-wave
+    // launch has <= 4 * G splits), then adds them in index order: one L2 round trip on the launch's critical tail instead
+    // of one per pair, same fixed summation order
+    const double2* p = reinterpret_cast<const double2*>(sg.partials) + tl.c * sg.splits;   // 16-byte aligned: workspace layouts keep it so
+    for (int base = tg; base < sg.splits; base += 4 * G) {
+        double2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = base + k * G;
+            v[k] = i < sg.splits ? __ldcg(p + i) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) { a += v[k].x; b += v[k].y; }
+    }
     group_sum2<G, THREADS>(a, b, red);
     if (tg == 0) sg.counters[tl.c] = 0u;          // leave the workspace zeroed for the next call
     return true;

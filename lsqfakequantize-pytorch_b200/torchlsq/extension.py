@@ -498,7 +498,7 @@ _TAIL = ("int quant_min, int quant_max, int type_min, int type_max, bool use_gra
 def _register_extensions():
     global _lib_handle
     lib = _cabi.load()          # OSError / AttributeError when the native library is absent or stale
-    if lib.lsqb200_abi_version() != 1:
+    if lib.lsqb200_abi_version() != _cabi.ABI_VERSION:
         raise ImportError("libtorchlsq_b200.so has an unexpected ABI version")
     L = torch.library.Library("torchlsq", "DEF")
     L.define("_cuda_version() -> int")

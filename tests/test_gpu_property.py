@@ -66,6 +66,37 @@ def test_random_cases_match_oracle(case):
         assert torch.count_nonzero(gb).item() == 0
 
 
+@settings(max_examples=90, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(tensor_case(), st.sampled_from(["relu", "add_relu", "add"]))
+def test_random_prologue_cases_match_oracle(case, prologue):
+    """Fused prologues over random shapes, axes, ranges, parameters, dtypes and modes: C ABI vs the oracle's
+    restatement of the separate passes (torch.relu / a + b -> reference op -> autograd)."""
+    from torchlsq import _cabi
+    shape, axis, per_channel, dt, (qmin, qmax, tmin, tmax), mode, use_gs, gscaler, seed = case
+    code = {"relu": _cabi.PRE_RELU, "add_relu": _cabi.PRE_ADD_RELU, "add": _cabi.PRE_ADD}[prologue]
+    relu = prologue != "add"
+    gen = torch.Generator().manual_seed(seed)
+    n = int(np.prod(shape))
+    spread = float(torch.rand(1, generator=gen)) * 4 + 0.1
+    x = (torch.randn(n, generator=gen) * spread).to(dt).to(U.DEV)
+    x2 = (torch.randn(n, generator=gen) * spread * 0.7).to(dt).to(U.DEV) if prologue != "relu" else None
+    g = torch.randn(n, generator=gen).to(dt).to(U.DEV)
+    outer, C, inner = geometry(shape, axis) if per_channel else (1, 1, n)
+    nparam = C if per_channel else 1
+    s = (0.005 + 0.1 * torch.rand(nparam, generator=gen)) * torch.where(torch.rand(nparam, generator=gen) < 0.1, -1.0, 1.0)
+    b = torch.randn(nparam, generator=gen) * (0.0 if mode == "sym" else 1.0)
+    s, b = s.to(U.DEV), b.to(U.DEV)
+    q = U.qa(qmin, qmax, tmin, tmax, use_gs, gscaler, sym=(mode == "sym"), eval_mode=(mode == "eval"), init_mode=(mode == "init"))
+    y = U.fwd(x, s, b, q, outer, C, inner, per_channel, prologue=code, x2=x2)
+    assert U.same_bits(y, U.oracle_fwd(x, s, b, q, outer, C, inner, per_channel, relu=relu, x2=x2))
+    gx, gs, gb = U.bwd(g, x, s, b, q, outer, C, inner, per_channel, prologue=code, x2=x2)
+    ogx, ogs, ogb, ms, mb = U.oracle_bwd(g, x, s, b, q, outer, C, inner, per_channel, relu=relu, x2=x2)
+    assert U.same_bits(gx, ogx)
+    rel = 1e-6 if dt == torch.float32 else 1e-5
+    U.assert_grads_close(gs, ogs, ms, rel, "gscale")
+    U.assert_grads_close(gb, ogb, mb, rel, "gshift")
+
+
 def test_cuda_graph_capture_and_replay():
     """forward + backward of two sites captured into one CUDA graph and replayed on new data."""
     from torchlsq import _cabi
