@@ -230,3 +230,77 @@ def test_meta_tensors_flow_through_the_ops():
     with pytest.raises(RuntimeError, match="not consistent"):
         torch.ops.torchlsq.lsq(x.detach(), torch.empty(5, device="meta"), torch.empty(5, device="meta"), 0, 127, 0, 255, 1, True, 1.0,
                                True, True, False, False)
+
+
+# ---- prologue fusion, host side: everything that needs no kernel ---------------------------------------------
+def test_fused_prologue_functions_have_no_cpu_path_and_check_arguments():
+    from torchlsq.functional import lsq_add, lsq_add_relu, lsq_relu
+    x, s, b = torch.randn(4, 8), torch.tensor([0.1]), torch.tensor([0.0])
+    for fn, args in ((lsq_relu, (x,)), (lsq_add_relu, (x, x)), (lsq_add, (x, x))):
+        with pytest.raises(RuntimeError, match="CUDA"):
+            fn(*args, s, b, 0, 127)
+        with pytest.raises(RuntimeError, match="1-D"):
+            fn(*args, torch.tensor(0.1), b, 0, 127)
+    with pytest.raises(AssertionError):
+        lsq_relu(x, s, b, 1, 127, is_affine=False)
+
+
+def test_module_fuse_relu_paths_that_return_the_input():
+    """debug mode, the parameter-creating first call and a disabled fake-quant hand back relu(x) (and relu(a + b) for
+    forward_add) - exactly what Sequential(ReLU(), LSQFakeQuantizer()) would."""
+    x, y = torch.randn(4, 6), torch.randn(4, 6)
+    m = LSQFakeQuantizer(None, 'activation', init_mode='learnable', fuse_relu=True, debug_mode=True)
+    assert torch.equal(m(x), torch.relu(x)) and torch.equal(m.forward_add(x, y), torch.relu(x + y))
+    assert torch.equal(m.forward_add(x, y, relu=False), x + y)
+    m = LSQFakeQuantizer(None, 'activation', init_mode='learnable', fuse_relu=True)
+    assert torch.equal(m(x), torch.relu(x)) and m._initialized          # first call: creates scale / shift, returns relu(x)
+    m.disable_fake_quant()
+    m.disable_observer()
+    assert torch.equal(m(x), torch.relu(x)) and torch.equal(m.forward_add(x, y), torch.relu(x + y))
+    plain = LSQFakeQuantizer(None, 'activation', init_mode='learnable')
+    assert plain.fuse_relu is False and torch.equal(plain(x), x)
+
+
+def test_fuse_prologues_patches_instances_only():
+    import copy
+    import torch.ao.quantization as tq
+    import torch.nn as nn
+    from torch.ao.nn.quantized import FloatFunctional
+    from torchlsq.fusion import fuse_prologues, unfuse_prologues
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1, self.bn1, self.relu1 = nn.Conv2d(4, 4, 3, padding=1, bias=False), nn.BatchNorm2d(4), nn.ReLU()
+            self.conv2, self.bn2 = nn.Conv2d(4, 4, 3, padding=1, bias=False), nn.BatchNorm2d(4)
+            self.fc, self.fc_relu = nn.Linear(4, 4), nn.ReLU()
+            self.skip, self.other = FloatFunctional(), FloatFunctional()
+            self.quant, self.dequant = tq.QuantStub(), tq.DeQuantStub()
+
+        def forward(self, x):
+            x = self.quant(x)
+            y = self.bn2(self.conv2(self.relu1(self.bn1(self.conv1(x)))))
+            return self.dequant(self.skip.add_relu(y, x))
+
+    m = Block().train()
+    m.qconfig = tq.QConfig(activation=LSQFakeQuantizer.with_args(observer=tq.MovingAverageMinMaxObserver, otype='activation'),
+                           weight=LSQFakeQuantizer.with_args(observer=None, otype='weight', dtype=torch.qint8,
+                                                             qscheme=torch.per_channel_symmetric, init_mode='learnable'))
+    m.other.qconfig = tq.QConfig(activation=tq.FakeQuantize.with_args(observer=tq.MovingAverageMinMaxObserver),
+                                 weight=tq.default_weight_fake_quant)           # not ours: must be left alone
+    tq.fuse_modules_qat(m, [['conv1', 'bn1', 'relu1'], ['conv2', 'bn2'], ['fc', 'fc_relu']], inplace=True)
+    tq.prepare_qat(m, inplace=True)
+    types_before = [type(x) for x in m.modules()]
+    assert fuse_prologues(m) == {"relu": 2, "residual": 1}                      # ConvBnReLU2d, LinearReLU; skip
+    assert fuse_prologues(m) == {"relu": 0, "residual": 0}                      # idempotent
+    assert [type(x) for x in m.modules()] == types_before                       # convert() keys on module types
+    assert m.conv1.activation_post_process.fuse_relu and m.fc.activation_post_process.fuse_relu
+    assert not m.conv2.activation_post_process.fuse_relu                        # ConvBn2d has no ReLU to fold
+    assert "add_relu" in m.skip.__dict__ and "add_relu" not in m.other.__dict__
+    # the patched forward is the parent's (no F.relu): negative outputs survive until the quantizer
+    m.conv1.activation_post_process.debug_mode = True
+    m2 = copy.deepcopy(m)                                                       # patches follow a deep copy and bind to the copy
+    assert m2.conv1.forward.__self__ is m2.conv1 and m2.skip.add_relu.__self__ is m2.skip
+    assert unfuse_prologues(m) == 3
+    assert "forward" not in m.conv1.__dict__ and "add_relu" not in m.skip.__dict__ and not m.conv1.activation_post_process.fuse_relu
+    assert fuse_prologues(m, relu=False) == {"relu": 0, "residual": 1}
