@@ -472,7 +472,10 @@ class LSQFakeQuantizer(ObserverBase):
             tail = (self.scale, self.shift, self.quant_min, self.quant_max, tmin, tmax,
                     self.ch_axis, self.use_grad_scaling, self.grad_scaler, self.is_affine, self.is_perchannel)
             if pending:
-                if x.is_cuda and x.dtype != torch.float64 and self.scale.dtype == torch.float32:
+                fusable = x.is_cuda and x.dtype != torch.float64 and self.scale.dtype == torch.float32
+                if x2 is not None:       # broadcasting / type-promoting adds keep ATen's semantics: materialise them
+                    fusable = fusable and x2.shape == x.shape and x2.dtype == x.dtype and x2.device == x.device
+                if fusable:
                     # steady state: the prologue runs inside the fake-quant kernels
                     if x2 is None:
                         return lsq_relu(x, *tail, eval_mode=(not full_lsq), init_mode=bool(backprop_init))

@@ -206,3 +206,21 @@ def test_plan_with_residual_sites_matches_calls():
         assert torch.equal(st.y, y) and torch.equal(st.gx, gx)
         assert torch.equal(st.gscale, gs) and torch.equal(st.gshift, gb)
     plan.close()
+
+
+def test_module_forward_add_falls_back_for_broadcast_or_promoting_adds():
+    """forward_add with operands ATen would broadcast / type-promote keeps ATen's semantics (separate add) - same values as
+    the module applied to relu(a + b); matching operands take the fused kernels and give the same bits."""
+    from torchlsq import LSQFakeQuantizer
+    m = LSQFakeQuantizer(None, "activation", init_mode="learnable", init_batches=1, init_scale=0.05).to(U.DEV)
+    a = torch.randn(4, 8, 6, 6, device=U.DEV)
+    m(a)                                                   # creates the parameters
+    m(a)                                                   # leaves the init window
+    m.eval()
+    bias = torch.randn(1, 8, 1, 1, device=U.DEV)
+    with torch.no_grad():
+        assert torch.equal(m.forward_add(a, bias), m(torch.relu(a + bias)))
+        assert torch.equal(m.forward_add(a, bias.expand_as(a).contiguous()), m(torch.relu(a + bias)))     # fused path, same bits
+        h = a.half()
+        assert torch.equal(m.forward_add(h, bias), m(torch.relu(h + bias)))                              # promotes to float32
+        assert torch.equal(m.forward_add(a, bias, relu=False), m(a + bias))
