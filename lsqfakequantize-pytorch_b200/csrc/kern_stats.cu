@@ -18,6 +18,20 @@ KernelFn pick(int nw, int group) {
     }
 }
 }  // namespace
+namespace {
+template <int U, int MB>
+KernelFn rowstats(int xdtype) {
+    if (xdtype == DT_F32) return lsq_rowstats_kernel<float, kThreads, U, kLd, MB>;
+    if (xdtype == DT_BF16) return lsq_rowstats_kernel<__nv_bfloat16, kThreads, U, kLd, MB>;
+    return lsq_rowstats_kernel<__half, kThreads, U, kLd, MB>;
+}
+}  // namespace
+// variant (Tuning::rowstats): 1 = four units in flight per lane, 4 CTAs/SM; 2 = two units, 6 CTAs/SM; 3 = one unit, 8 CTAs/SM
+KernelFn get_rowstats_kernel(int xdtype, int variant) {
+    if (variant == 2) return rowstats<2, 6>(xdtype);
+    if (variant == 3) return rowstats<1, 8>(xdtype);
+    return rowstats<kRowStatsUnroll, kRowStatsMinBlocks>(xdtype);
+}
 KernelFn get_stats_kernel(int xdtype, int nw, int group) {
     if (xdtype == DT_F32) return pick<float>(nw, group);
     if (xdtype == DT_BF16) return pick<__nv_bfloat16>(nw, group);

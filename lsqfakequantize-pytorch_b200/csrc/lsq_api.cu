@@ -355,6 +355,7 @@ struct lsqb200_plan {
     std::vector<long long> stats_offset;   // running sum of C (or 1) per segment
     void* workspace = nullptr;             // counters + partials for every split segment
     float** stats_slot = nullptr;
+    const float* stats_uploaded_for = nullptr;   // output buffer the device-side statistics tables currently point at
     int device = 0;
 };
 
@@ -382,7 +383,8 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         else if (kind == K_BWD) { variant = bmode_of(&s.q); k = get_bwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
         else {
             if (s.xdtype == DT_F64) continue;   // no float64 statistics (the module cannot hold float64 weights): slot left untouched
-            k = get_stats_kernel(s.xdtype, g.nw, g.group);
+            if (rowstats_eligible(g, s.xdtype) && tn.rowstats) { variant = 1; k = get_rowstats_kernel(s.xdtype, tn.rowstats); }
+            else k = get_stats_kernel(s.xdtype, g.nw, g.group);
         }
         if (!k) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
         const ClassKey key{s.xdtype, kind == K_STATS ? 0 : mode, g.nw, variant, g.group};
@@ -497,6 +499,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "col_waves_bwd") g_tuning.col_waves_bwd = v > 0 ? v : 1;
         else if (k == "col_tma") g_tuning.col_tma = (v >= 0 && v <= 3) ? v : 0;
         else if (k == "column_max_row_bytes") g_tuning.column_max_row_bytes = v;
+        else if (k == "rowstats") g_tuning.rowstats = (v >= 0 && v <= 3) ? v : 2;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;
     }
@@ -585,7 +588,7 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
                          C > 1, &q);
     a.stats_out = scale_out;
     const Seg seg = make_seg(a, g, partials, counters, 0);
-    KernelFn k = get_stats_kernel(xdtype, g.nw, g.group);
+    KernelFn k = (rowstats_eligible(g, xdtype) && tuning().rowstats) ? get_rowstats_kernel(xdtype, tuning().rowstats) : get_stats_kernel(xdtype, g.nw, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
@@ -721,9 +724,12 @@ int lsqb200_plan_backward(lsqb200_plan* plan, void* stream) {
 
 int lsqb200_plan_weight_init_stats(lsqb200_plan* plan, float* scale_out, void* stream) {
     if (!plan || !scale_out) return fail(LSQB200_ERR_PLAN, "NULL plan or output");
-    // tables are (re)uploaded with the output pointers patched in; this is an init-time call
+    // tables are uploaded with the output pointers patched in (again only when the output buffer changes); this is an init-time call
+    const bool same_out = plan->stats_uploaded_for == scale_out;
+    plan->stats_uploaded_for = scale_out;
     for (auto& c : plan->stats) {
         if (c.host.empty()) continue;
+        if (same_out && c.dev) continue;
         for (auto& s : c.host) s.stats_out = scale_out + plan->stats_offset[(size_t)s.chan_stride];
         if (!c.dev) {
             cudaError_t e = cudaMalloc(&c.dev, c.host.size() * sizeof(Seg));

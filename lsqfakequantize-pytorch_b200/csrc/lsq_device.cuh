@@ -752,6 +752,17 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
 // mu +- 3 sigma weight-init statistics (observers.py:329-337): ONE read of w.
 // Shifted sums in double: S1 = sum(w - p), S2 = sum((w - p)^2), p = first element of the channel.
 // ---------------------------------------------------------------------------------------------
+// scale = max(|mu - 3 sd|, |mu + 3 sd|) / 2^bitness from the shifted sums S1 = sum(w - p), S2 = sum((w - p)^2) of K elements
+__device__ __forceinline__ float stats_scale(double s1, double s2, float pivot, double K, float denom) {
+    const double mean = (double)pivot + s1 / K;
+    double var = (s2 - s1 * s1 / K) / (K - 1.0);                   // unbiased (torch.std default); K == 1 -> NaN
+    if (var < 0.0) var = 0.0;
+    const float mu = (float)mean, sd = (float)sqrt(var);
+    const float lo = fabsf(__fsub_rn(mu, __fmul_rn(3.0f, sd)));
+    const float hi = fabsf(__fadd_rn(mu, __fmul_rn(3.0f, sd)));
+    return __fdiv_rn(fmaxf(lo, hi), denom);
+}
+
 template <typename T, int NW, int G, int THREADS, int UNROLL, int LD, int MINB = 1>
 __global__ void __launch_bounds__(THREADS, MINB)
 lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
@@ -822,17 +833,70 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
         }
     }
     if (!channel_finish<G, THREADS>(sg, tl, s1, s2, red, &last_flag[grp], tg)) continue;
-    if (tg == 0) {
-        const double K = (double)sg.chan_elems;
-        const double mean = (double)pivot + s1 / K;
-        double var = (s2 - s1 * s1 / K) / (K - 1.0);               // unbiased (torch.std default); K == 1 -> NaN
-        if (var < 0.0) var = 0.0;
-        const float mu = (float)mean, sd = (float)sqrt(var);
-        const float lo = fabsf(__fsub_rn(mu, __fmul_rn(3.0f, sd)));
-        const float hi = fabsf(__fadd_rn(mu, __fmul_rn(3.0f, sd)));
-        sg.stats_out[tl.c] = __fdiv_rn(fmaxf(lo, hi), sg.stats_denom);
-    }
+    if (tg == 0) sg.stats_out[tl.c] = stats_scale(s1, s2, pivot, (double)sg.chan_elems, sg.stats_denom);
     }   // tiles of this group
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight rows, the statistics kernel's everyday case (every conv / linear weight with axis 0: contiguous rows of a few
+// hundred to a few thousand elements, 32-byte aligned): ONE WARP PER ROW with nothing but the row walk in the loop.
+// The general kernel above spends ~600 warp instructions per row on descriptor staging, tile geometry, peel logic and the
+// unit walker - more than the arithmetic of a 4 KB row (ncu, profiles/); here the descriptor fields are read straight from
+// the plan table (plan-time constants in L2), the row is base + lane*32 B + k*1 KB, and UNROLL 256-bit loads per lane
+// are in flight (two at 6 CTAs/SM measured best: rows are short, more resident warps beat deeper prefetch).  Same arithmetic as lsq_stats_kernel (fp32 within a unit, fp64 across units, shifted by the row's first
+// element), so the two kernels agree to the last bit of the fp64 sums' rounding.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int THREADS, int UNROLL, int LD, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_rowstats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                    long long total_tiles) {
+    constexpr int NW = 8, VEC = UnitOf<T, NW>::VEC, UB = 32;
+    const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    const long long gtile = (long long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    if (gtile >= total_tiles) return;
+    const Seg* sg = &single;
+    if (table != nullptr) {                       // plan tables are written at plan creation only: safe to read before the wait
+        int want;
+        if (tile_seg != nullptr) want = tile_seg[gtile];
+        else {
+            int lo = 0, hi = nseg - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (table[mid].tile_begin <= gtile) lo = mid; else hi = mid - 1; }
+            want = lo;
+        }
+        sg = &table[want];
+    }
+    const long long c = gtile - sg->tile_begin, inner = sg->inner;
+    const int units = (int)(inner / VEC);         // <= Tuning::warp_units, row bytes are a multiple of 32 (host check)
+    const T* row = reinterpret_cast<const T*>(sg->x) + c * inner;
+    float* out = sg->stats_out;
+    const float denom = sg->stats_denom;
+    pdl_wait();
+    const float pivot = ElemTraits<T>::to_f(row[0]);
+    const char* p = reinterpret_cast<const char*>(row) + lane * UB;
+    double s1 = 0.0, s2 = 0.0;
+    for (int u = lane; u < units; u += 32 * UNROLL) {
+        Raw<NW> r[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++)          // lanes past the row end re-read their first unit: loads stay unconditional
+            r[k] = ld_unit<LD, NW>(p + (u + 32 * k < units ? k : 0) * (32 * UB));
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            if (u + 32 * k >= units) continue;
+            float f[VEC];
+            unpack_unit<T, NW>(r[k], f);
+            float u1 = 0.f, u2 = 0.f;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                const float d = __fsub_rn(f[e], pivot);
+                u1 = __fadd_rn(u1, d); u2 = __fmaf_rn(d, d, u2);
+            }
+            s1 += (double)u1; s2 += (double)u2;
+        }
+        p += UNROLL * 32 * UB;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) out[c] = stats_scale(s1, s2, pivot, (double)inner, denom);
 }
 
 
