@@ -233,7 +233,8 @@ int forward_common(const void* x, const void* x2, void* y, const void* scale, co
     SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
     a.x2 = x2;
     const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
-    KernelFn k = get_fwd_kernel(xdt, mode, g.nw, q->init_mode != 0, g.group);
+    KernelFn k = (mode == M_FP32 && tuning().rowkernels && rowstats_eligible(g, xdt)) ? get_rowfwd_kernel(xdt, q->init_mode != 0)
+                                                                                      : get_fwd_kernel(xdt, mode, g.nw, q->init_mode != 0, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 
@@ -303,7 +304,8 @@ int backward_common(const void* grad, const void* x, const void* x2, void* gx, c
     SegArgs a = seg_args(x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, xdt, pdt, per_channel, q);
     a.x2 = x2;
     const Seg seg = make_seg(a, g, partials, counters, 0);
-    KernelFn k = get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
+    KernelFn k = (mode == M_FP32 && tuning().rowkernels && rowstats_eligible(g, xdt)) ? get_rowbwd_kernel(xdt, bmode_of(q))
+                                                                                      : get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, st);
 }
 
@@ -379,8 +381,16 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         Geometry g = plan_geometry(s.outer, s.C, s.inner, s.xdtype, kind, al, tuning_for_mode(tn, mode));
         int variant = 0;
         KernelFn k = nullptr;
-        if (kind == K_FWD) { variant = s.q.init_mode != 0; k = get_fwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
-        else if (kind == K_BWD) { variant = bmode_of(&s.q); k = get_bwd_kernel(s.xdtype, mode, g.nw, variant, g.group); }
+        const bool lean = mode == M_FP32 && tn.rowkernels && rowstats_eligible(g, s.xdtype);   // aligned weight rows: warp-per-row kernels
+        if (kind == K_FWD) {
+            variant = s.q.init_mode != 0;
+            k = lean ? get_rowfwd_kernel(s.xdtype, variant != 0) : get_fwd_kernel(s.xdtype, mode, g.nw, variant, g.group);
+            if (lean) variant += 16;
+        } else if (kind == K_BWD) {
+            variant = bmode_of(&s.q);
+            k = lean ? get_rowbwd_kernel(s.xdtype, variant) : get_bwd_kernel(s.xdtype, mode, g.nw, variant, g.group);
+            if (lean) variant += 16;
+        }
         else {
             if (s.xdtype == DT_F64) continue;   // no float64 statistics (the module cannot hold float64 weights): slot left untouched
             if (rowstats_eligible(g, s.xdtype) && tn.rowstats) { variant = 1; k = get_rowstats_kernel(s.xdtype, tn.rowstats); }
@@ -499,6 +509,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "col_waves_bwd") g_tuning.col_waves_bwd = v > 0 ? v : 1;
         else if (k == "col_tma") g_tuning.col_tma = (v >= 0 && v <= 3) ? v : 0;
         else if (k == "column_max_row_bytes") g_tuning.column_max_row_bytes = v;
+        else if (k == "rowkernels") g_tuning.rowkernels = v;
         else if (k == "rowstats") g_tuning.rowstats = (v >= 0 && v <= 3) ? v : 2;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;

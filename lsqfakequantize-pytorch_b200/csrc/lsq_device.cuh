@@ -837,6 +837,28 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
     }   // tiles of this group
 }
 
+// Row c of a contiguous (C, inner) tensor whose base is 32-byte aligned: scalar head up to the first 32-byte boundary, whole
+// 256-bit units, scalar tail.  Rows that are 32-byte multiples (all but a first conv layer's) have neither head nor tail.
+template <typename T, int VEC>
+struct RowGeom {
+    long long e0;          // element index of the row's first element
+    int head, units, tail; // elements, units, elements
+    __device__ __forceinline__ void init(long long c, long long inner) {
+        e0 = c * inner;
+        const int mis = (int)((e0 * (long long)sizeof(T)) & 31);
+        long long h = mis ? (32 - mis) / (int)sizeof(T) : 0;
+        if (h > inner) h = inner;
+        head = (int)h;
+        const long long body = inner - h;
+        units = (int)(body / VEC);
+        tail = (int)(body - (long long)units * VEC);
+    }
+    // i-th scalar element (0 <= i < head + tail) -> element index
+    __device__ __forceinline__ long long scalar_elem(int i) const {
+        return i < head ? e0 + i : e0 + head + (long long)units * VEC + (i - head);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Weight rows, the statistics kernel's everyday case (every conv / linear weight with axis 0: contiguous rows of a few
 // hundred to a few thousand elements, 32-byte aligned): ONE WARP PER ROW with nothing but the row walk in the loop.
@@ -867,14 +889,20 @@ lsq_rowstats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ 
         sg = &table[want];
     }
     const long long c = gtile - sg->tile_begin, inner = sg->inner;
-    const int units = (int)(inner / VEC);         // <= Tuning::warp_units, row bytes are a multiple of 32 (host check)
-    const T* row = reinterpret_cast<const T*>(sg->x) + c * inner;
+    RowGeom<T, VEC> rg;
+    rg.init(c, inner);
+    const int units = rg.units;                   // <= Tuning::warp_units
+    const T* xp = reinterpret_cast<const T*>(sg->x);
     float* out = sg->stats_out;
     const float denom = sg->stats_denom;
     pdl_wait();
-    const float pivot = ElemTraits<T>::to_f(row[0]);
-    const char* p = reinterpret_cast<const char*>(row) + lane * UB;
+    const float pivot = ElemTraits<T>::to_f(xp[rg.e0]);
+    const char* p = reinterpret_cast<const char*>(xp + rg.e0 + rg.head) + lane * UB;
     double s1 = 0.0, s2 = 0.0;
+    for (int i = lane; i < rg.head + rg.tail; i += 32) {
+        const float d = __fsub_rn(ElemTraits<T>::to_f(xp[rg.scalar_elem(i)]), pivot);
+        s1 += (double)d; s2 += (double)__fmul_rn(d, d);
+    }
     for (int u = lane; u < units; u += 32 * UNROLL) {
         Raw<NW> r[UNROLL];
 #pragma unroll
@@ -899,6 +927,144 @@ lsq_rowstats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ 
     if (lane == 0) out[c] = stats_scale(s1, s2, pivot, (double)inner, denom);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Weight rows, forward and backward: the same lean warp-per-row shape as lsq_rowstats_kernel for the rows the plans of a
+// model consist of (every conv / linear weight with axis 0, 32-byte aligned rows of <= Tuning::warp_units units).  The
+// arithmetic is fq_forward / fq_backward<EXACT> exactly as in the warp-group instantiations of the general kernels (the
+// reference's fp32 terms bit for bit, summed in fp64); what is gone is the per-row descriptor staging, tile geometry, peel
+// logic and unit walker (~600 warp instructions per row, more than the work of a 4 KB row).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ const Seg* find_segment(const Seg& single, const Seg* table, const int* tile_seg, int nseg, long long gtile) {
+    if (table == nullptr) return &single;
+    if (tile_seg != nullptr) return &table[tile_seg[gtile]];
+    int lo = 0, hi = nseg - 1;                    // last segment with tile_begin <= gtile
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (table[mid].tile_begin <= gtile) lo = mid; else hi = mid - 1; }
+    return &table[lo];
+}
+
+template <typename T, int MODE, bool INIT, int THREADS, int UNROLL, int LD, int ST, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_rowfwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                  long long total_tiles) {
+    constexpr int NW = 8, VEC = UnitOf<T, NW>::VEC, UB = 32;
+    const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    const long long gtile = (long long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    if (gtile >= total_tiles) return;
+    const Seg* sg = find_segment(single, table, tile_seg, nseg, gtile);     // plan-time constants: readable before the wait
+    const long long c = gtile - sg->tile_begin, inner = sg->inner;
+    RowGeom<T, VEC> rg;
+    rg.init(c, inner);
+    const int units = rg.units;
+    const T* xp = reinterpret_cast<const T*>(sg->x);
+    T* yp = reinterpret_cast<T*>(sg->y);
+    const char* px = reinterpret_cast<const char*>(xp + rg.e0 + rg.head) + lane * UB;
+    char* py = reinterpret_cast<char*>(yp + rg.e0 + rg.head) + lane * UB;
+    const long long pidx = sg->per_channel ? c : 0;
+    pdl_wait();
+    Chan ch;
+    float sraw = 0.f, braw = 0.f;
+    if (!INIT) { sraw = load_param(sg->scale, pidx, sg->pdt); braw = load_param(sg->shift, pidx, sg->pdt); }
+    bool have = false;
+    if (rg.head + rg.tail > 0) {                  // rows that do not start / end on a 32-byte boundary (uniform per warp)
+        if (!INIT) { ch = make_chan<MODE>(sraw, braw, *sg); have = true; }
+        for (int i = lane; i < rg.head + rg.tail; i += 32) {
+            const long long e = rg.scalar_elem(i);
+            yp[e] = INIT ? xp[e] : ElemTraits<T>::from_f(fq_forward<MODE>(ElemTraits<T>::to_f(xp[e]), ch));
+        }
+    }
+    for (int u = lane; u < units; u += 32 * UNROLL) {
+        Raw<NW> r[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) r[k] = ld_unit<LD, NW>(px + (u + 32 * k < units ? k : 0) * (32 * UB));
+        if (!INIT && !have) { ch = make_chan<MODE>(sraw, braw, *sg); have = true; }    // after the first data loads are in flight
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            if (u + 32 * k >= units) continue;
+            if (INIT) { st_unit<ST, NW>(py + k * (32 * UB), r[k]); continue; }
+            float f[VEC];
+            unpack_unit<T, NW>(r[k], f);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) f[e] = fq_forward<MODE>(f[e], ch);
+            st_unit<ST, NW>(py + k * (32 * UB), pack_unit<T, NW>(f));
+        }
+        px += UNROLL * 32 * UB; py += UNROLL * 32 * UB;
+    }
+}
+
+template <typename T, int MODE, int BMODE, int THREADS, int UNROLL, int LD, int ST, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_rowbwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                  long long total_tiles) {
+    constexpr int NW = 8, VEC = UnitOf<T, NW>::VEC, UB = 32;
+    const int lane = threadIdx.x & 31;
+    pdl_trigger();
+    const long long gtile = (long long)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    if (gtile >= total_tiles) return;
+    const Seg* sg = find_segment(single, table, tile_seg, nseg, gtile);
+    const long long c = gtile - sg->tile_begin, inner = sg->inner;
+    RowGeom<T, VEC> rg;
+    rg.init(c, inner);
+    const int units = rg.units;
+    const T* xp = reinterpret_cast<const T*>(sg->x);
+    const T* gp = reinterpret_cast<const T*>(sg->g);
+    T* gxp = reinterpret_cast<T*>(sg->gx);
+    const long long row_off = (rg.e0 + rg.head) * (long long)sizeof(T) + lane * UB;
+    const char* px = reinterpret_cast<const char*>(sg->x) + row_off;
+    const char* pg = reinterpret_cast<const char*>(sg->g) + row_off;
+    char* pgx = sg->gx ? reinterpret_cast<char*>(sg->gx) + row_off : nullptr;
+    const long long pidx = sg->per_channel ? c : 0;
+    pdl_wait();
+    const float sraw = load_param(sg->scale, pidx, sg->pdt), braw = load_param(sg->shift, pidx, sg->pdt);
+    Chan ch;
+    bool have = false;
+    double accS = 0.0, accB = 0.0;
+    if (rg.head + rg.tail > 0) {                  // rows that do not start / end on a 32-byte boundary (uniform per warp)
+        ch = make_chan<MODE>(sraw, braw, *sg); have = true;
+        for (int i = lane; i < rg.head + rg.tail; i += 32) {
+            const long long e = rg.scalar_elem(i);
+            const float dx = fq_backward<MODE, BMODE, true>(ElemTraits<T>::to_f(gp[e]), ElemTraits<T>::to_f(xp[e]), ch, accS, accB);
+            if (gxp) gxp[e] = bmode_passthrough(BMODE) ? gp[e] : ElemTraits<T>::from_f(dx);
+        }
+    }
+    for (int u = lane; u < units; u += 32 * UNROLL) {
+        Raw<NW> xr[UNROLL], gr[UNROLL];
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            const int o = (u + 32 * k < units ? k : 0) * (32 * UB);
+            xr[k] = ld_unit<LD, NW>(px + o);
+            gr[k] = ld_unit<LD, NW>(pg + o);
+        }
+        if (!have) { ch = make_chan<MODE>(sraw, braw, *sg); have = true; }
+        double ls = 0.0, lb = 0.0;
+#pragma unroll
+        for (int k = 0; k < UNROLL; k++) {
+            if (u + 32 * k >= units) continue;
+            float fx[VEC], fg[VEC];
+            unpack_unit<T, NW>(xr[k], fx);
+            unpack_unit<T, NW>(gr[k], fg);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) fg[e] = fq_backward<MODE, BMODE, true>(fg[e], fx[e], ch, ls, lb);
+            if (pgx) {
+                if (bmode_passthrough(BMODE)) st_unit<ST, NW>(pgx + k * (32 * UB), gr[k]);
+                else st_unit<ST, NW>(pgx + k * (32 * UB), pack_unit<T, NW>(fg));
+            }
+        }
+        accS += ls; accB += lb;
+        px += UNROLL * 32 * UB; pg += UNROLL * 32 * UB;
+        if (pgx) pgx += UNROLL * 32 * UB;
+    }
+    if (!bmode_reduces(BMODE)) {                  // eval: exact zeros (lsq_kernel.h:143-144)
+        if (lane == 0) { store_param(sg->gscale, pidx, sg->pdt, 0.0); store_param(sg->gshift, pidx, sg->pdt, 0.0); }
+        return;
+    }
+    accS = warp_sum(accS); accB = warp_sum(accB);
+    if (lane == 0) {
+        store_param(sg->gscale, pidx, sg->pdt, accS * sg->gs);
+        store_param(sg->gshift, pidx, sg->pdt, sg->sym ? 0.0 : accB * sg->gs);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // Observer step (init_mode='observer', observers.py:446-449): ONE read of x gives the per-tensor /

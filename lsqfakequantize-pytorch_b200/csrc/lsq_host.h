@@ -89,6 +89,11 @@ inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int grou
     return get_bwd_kernel_bf16(mode, nw, bmode, group);
 }
 KernelFn get_stats_kernel(int xdtype, int nw, int group);
+// kern_rows.cu: lean warp-per-row forward / backward for aligned weight rows (M_FP32 arithmetic only)
+KernelFn get_rowfwd_kernel(int xdtype, bool init);
+KernelFn get_rowbwd_kernel(int xdtype, int bmode);
+constexpr int kRowUnrollFwd = 2, kRowMinBlocksFwd = 6;   // units in flight per lane, CTAs/SM
+constexpr int kRowUnrollBwd = 1, kRowMinBlocksBwd = 4;
 // weight rows (contiguous, 32-byte aligned, one warp each): see lsq_rowstats_kernel
 KernelFn get_rowstats_kernel(int xdtype, int variant);
 constexpr int kRowStatsUnroll = 4;       // variant 1: 256-bit loads in flight per lane
@@ -136,6 +141,7 @@ struct Tuning {
     int whole_waves = 1;        // round big-tensor tile counts to whole waves of resident CTAs
     int pdl = 1;                // launch with programmatic stream serialization (prologue overlaps predecessor's tail)
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
+ int rowkernels = 1;         // forward / backward over aligned weight rows: the lean warp-per-row kernels (0: the general warp-group kernels)
     int rowstats = 2;           // mu +- 3 sigma over aligned weight rows: the lean warp-per-row kernel, variant 1 / 2 / 3 (kern_stats.cu); 0: the general kernel
                                 // 54 ResNet-50 weights under ncu on B200: general kernel 34.5 us, variant 1 28.7, 2 25.2, 3 26.3
     // resident CTAs/SM the kernel family really gets (its __launch_bounds__): whole-wave rounding uses these.  The two-operand
@@ -162,10 +168,9 @@ struct Geometry {
 };
 
 inline int elem_size(int dt) { return dt == DT_F64 ? 8 : (dt == DT_F32 ? 4 : 2); }
-// statistics over contiguous channel rows that one warp owns and that start on 32-byte boundaries: the row kernel applies
+// contiguous channel rows that one warp owns, in tensors whose base pointers are 32-byte aligned: the lean row kernels apply
 inline bool rowstats_eligible(const Geometry& g, int xdtype) {
-    return g.regime == 0 && g.group == 32 && g.nw == 8 && g.splits == 1 && xdtype != DT_F64 &&
-           (g.inner * elem_size(xdtype)) % 32 == 0 && g.inner > 0;
+    return g.regime == 0 && g.group == 32 && g.nw == 8 && g.splits == 1 && xdtype != DT_F64 && g.inner > 0;   // rows need not be 32-byte multiples: scalar head / tail
 }
 
 inline Geometry plan_geometry(long long outer, long long C, long long inner, int xdtype, int kind,

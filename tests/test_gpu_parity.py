@@ -205,6 +205,7 @@ def test_empty_and_errors():
 CH_SHAPES = [
     ((6, 4, 3, 3), 0), ((64, 3, 7, 7), 0),          # weight rows, K = 36 / 147 (rows lose 16 B alignment)
     ((256, 64, 1, 1), 0), ((1000, 2048), 0), ((512, 512, 3, 3), 0),
+    ((33, 1, 5, 5), 0), ((10, 37), 0), ((7, 1), 0), ((5, 8200), 0),   # rows shorter than a unit, single-element rows, rows past the warp-group limit
     ((8, 32, 14, 14), 1), ((4, 64, 56, 56), 1), ((16, 1024, 28, 28), 1), ((3, 5, 7), 1), ((3, 5, 7), 2),
     ((32, 1000), 1), ((2, 3, 224, 224), 1), ((64, 256, 7, 7), 1),
     # short channel rows -> column-layout kernels: channels-last, 7x7 / 14x14 maps, ragged unit/channel overlap
@@ -232,6 +233,30 @@ def test_channel_fwd_bwd(dt, shape, axis):
     U.assert_grads_close(gb, ogb, mb, rel, "gshift")
     _, gs2, gb2 = U.bwd(g, x, s, b, q, outer, C, inner, True)
     assert torch.equal(gs, gs2) and torch.equal(gb, gb2)
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("mode", ["init", "eval", "eval_init", "sym", "no_gx"])
+def test_weight_rows_with_head_and_tail_all_modes(dt, mode):
+    """Lean warp-per-row kernels on rows that neither start nor end on a 32-byte boundary (a first conv layer's 7x7x3 rows)."""
+    shape = (64, 3, 7, 7)
+    n = int(np.prod(shape))
+    x, g = _mk(n, DT[dt], seed=77, scale=0.6)
+    outer, C, inner = geometry(shape, 0)
+    gen = torch.Generator().manual_seed(5)
+    s = (0.02 + 0.02 * torch.rand(C, generator=gen)).to(U.DEV)
+    b = (-torch.rand(C, generator=gen)).to(U.DEV) * (0.0 if mode == "sym" else 1.0)
+    kw = dict(init=dict(init_mode=True), eval=dict(eval_mode=True), eval_init=dict(eval_mode=True, init_mode=True),
+              sym=dict(qmin=-64, qmax=63, tmin=-128, tmax=127, sym=True), no_gx=dict())[mode]
+    q = U.qa(**kw)
+    assert U.same_bits(U.fwd(x, s, b, q, outer, C, inner, True), U.oracle_fwd(x, s, b, q, outer, C, inner, True))
+    gx, gs, gb = U.bwd(g, x, s, b, q, outer, C, inner, True, want_gx=(mode != "no_gx"))
+    ogx, ogs, ogb, ms, mb = U.oracle_bwd(g, x, s, b, q, outer, C, inner, True)
+    if mode != "no_gx":
+        assert U.same_bits(gx, ogx)
+    rel = 1e-6 if dt == "f32" else 1e-5
+    U.assert_grads_close(gs, ogs, ms, rel, "gscale")
+    U.assert_grads_close(gb, ogb, mb, rel, "gshift")
 
 
 def test_channel_weights_symmetric_qint8():
