@@ -118,6 +118,24 @@ int launch(KernelFn k, const Seg& seg, const Seg* table, const int* tile_seg, in
     return 0;
 }
 
+int launch_flat(FlatKernelFn k, const Seg& seg, long long grid, cudaStream_t st) {
+    if (grid <= 0) return 0;
+    if (grid > 2147483647LL) return fail(LSQB200_ERR_ARG, "tensor too large for one launch");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tuning().pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, k, seg);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return 0;
+}
+
 size_t param_size(int pdt) { return pdt == DT_F64 ? 8 : (pdt == DT_F32 ? 4 : 2); }
 
 // ---- column-layout path (short channel rows: channels-last, 7x7 / 14x14 maps) ------------------
@@ -233,6 +251,8 @@ int forward_common(const void* x, const void* x2, void* y, const void* scale, co
     SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
     a.x2 = x2;
     const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
+    if (mode == M_FP32 && tuning().flatkernels && flat_eligible(g, xdt))
+        return launch_flat(get_flatfwd_kernel(xdt, q->init_mode != 0), seg, g.grid, (cudaStream_t)stream);
     KernelFn k = (mode == M_FP32 && tuning().rowkernels && rowstats_eligible(g, xdt)) ? get_rowfwd_kernel(xdt, q->init_mode != 0)
                                                                                       : get_fwd_kernel(xdt, mode, g.nw, q->init_mode != 0, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
@@ -304,6 +324,8 @@ int backward_common(const void* grad, const void* x, const void* x2, void* gx, c
     SegArgs a = seg_args(x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, xdt, pdt, per_channel, q);
     a.x2 = x2;
     const Seg seg = make_seg(a, g, partials, counters, 0);
+    if (mode == M_FP32 && tuning().flatkernels >= 2 && flat_eligible(g, xdt))
+        return launch_flat(get_flatbwd_kernel(xdt, bmode_of(q)), seg, g.grid, st);
     KernelFn k = (mode == M_FP32 && tuning().rowkernels && rowstats_eligible(g, xdt)) ? get_rowbwd_kernel(xdt, bmode_of(q))
                                                                                       : get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, st);
@@ -510,6 +532,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "col_tma") g_tuning.col_tma = (v >= 0 && v <= 3) ? v : 0;
         else if (k == "column_max_row_bytes") g_tuning.column_max_row_bytes = v;
         else if (k == "rowkernels") g_tuning.rowkernels = v;
+        else if (k == "flatkernels") g_tuning.flatkernels = v;
         else if (k == "rowstats") g_tuning.rowstats = (v >= 0 && v <= 3) ? v : 2;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;

@@ -1067,6 +1067,109 @@ lsq_rowbwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ ta
 }
 
 // ---------------------------------------------------------------------------------------------
+// Per-tensor sites launched one at a time (the activation sites of a training step): the lean form of the general kernels
+// for ONE contiguous channel in 32-byte aligned buffers.  Same tiles, same interleaved unit <-> thread mapping, same
+// arithmetic and the same fixed-order reduction as lsq_fwd_kernel / lsq_bwd_kernel - results are bit-identical - but the
+// descriptor stays in the constant bank (no shared-memory staging and barriers), there is no tile geometry, peel or walker
+// state to set up (~600 warp instructions per CTA before the first load, 1-1.5 us of every launch's ramp), and the loop
+// advances one pointer instead of a (row, column) pair.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, bool INIT, int THREADS, int LD, int ST, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_flatfwd_kernel(const __grid_constant__ Seg sg) {
+    using Tr = ElemTraits<T>;
+    constexpr int NW = 8, VEC = UnitOf<T, NW>::VEC, UB = 32;
+    pdl_trigger();
+    const long long units = sg.inner / VEC;
+    const long long stride = (long long)gridDim.x * THREADS;
+    long long u = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const char* px = reinterpret_cast<const char*>(sg.x) + u * UB;
+    char* py = reinterpret_cast<char*>(sg.y) + u * UB;
+    const long long sb = stride * UB;
+    pdl_wait();                                   // first touch of tensor / parameter memory is below
+    LazyChan<MODE> lch;
+    lch.issue(sg, 0);
+    if (blockIdx.x == 0) {                        // the < VEC elements behind the last whole unit
+        const T* xp = reinterpret_cast<const T*>(sg.x);
+        T* yp = reinterpret_cast<T*>(sg.y);
+        for (long long e = units * VEC + threadIdx.x; e < sg.inner; e += THREADS)
+            yp[e] = INIT ? xp[e] : Tr::from_f(fq_forward<MODE>(Tr::to_f(xp[e]), lch.get(sg)));
+    }
+    for (; u < units; u += stride) {
+        const Raw<NW> xr = ld_unit<LD, NW>(px);
+        if (INIT) st_unit<ST, NW>(py, xr);
+        else {
+            const Chan& ch = lch.get(sg);
+            float f[VEC];
+            unpack_unit<T, NW>(xr, f);
+#pragma unroll
+            for (int e = 0; e < VEC; e++) f[e] = fq_forward<MODE>(f[e], ch);
+            st_unit<ST, NW>(py, pack_unit<T, NW>(f));
+        }
+        px += sb; py += sb;
+    }
+}
+
+template <typename T, int MODE, int BMODE, int THREADS, int LD, int ST, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_flatbwd_kernel(const __grid_constant__ Seg sg) {
+    using Tr = ElemTraits<T>;
+    constexpr int NW = 8, VEC = UnitOf<T, NW>::VEC, UB = 32;
+    __shared__ double red[64];
+    __shared__ int last_flag;
+    pdl_trigger();
+    const long long units = sg.inner / VEC;
+    const long long stride = (long long)gridDim.x * THREADS;
+    long long u = (long long)blockIdx.x * THREADS + threadIdx.x;
+    const char* px = reinterpret_cast<const char*>(sg.x) + u * UB;
+    const char* pg = reinterpret_cast<const char*>(sg.g) + u * UB;
+    char* pgx = sg.gx ? reinterpret_cast<char*>(sg.gx) + u * UB : nullptr;
+    const long long sb = stride * UB;
+    pdl_wait();                                   // first touch of tensor / parameter memory is below
+    LazyChan<MODE> lch;
+    lch.issue(sg, 0);
+    double accS = 0.0, accB = 0.0;
+    if (blockIdx.x == 0) {                        // the < VEC elements behind the last whole unit (exact terms, as the general kernel's peel)
+        const T* xp = reinterpret_cast<const T*>(sg.x);
+        const T* gp = reinterpret_cast<const T*>(sg.g);
+        T* gxp = reinterpret_cast<T*>(sg.gx);
+        for (long long e = units * VEC + threadIdx.x; e < sg.inner; e += THREADS) {
+            const float dx = fq_backward<MODE, BMODE, true>(Tr::to_f(gp[e]), Tr::to_f(xp[e]), lch.get(sg), accS, accB);
+            if (gxp) gxp[e] = bmode_passthrough(BMODE) ? gp[e] : Tr::from_f(dx);
+        }
+    }
+    for (; u < units; u += stride) {
+        const Raw<NW> xr = ld_unit<LD, NW>(px);
+        const Raw<NW> gr = ld_unit<LD, NW>(pg);
+        const Chan& ch = lch.get(sg);
+        float fx[VEC], fg[VEC];
+        unpack_unit<T, NW>(xr, fx);
+        unpack_unit<T, NW>(gr, fg);
+        float ls = 0.f, lb = 0.f;                 // fp32 partial over one unit's <= 16 terms, then promoted (as lsq_bwd_kernel)
+#pragma unroll
+        for (int e = 0; e < VEC; e++) fg[e] = fq_backward<MODE, BMODE, false>(fg[e], fx[e], ch, ls, lb);
+        if (pgx) {
+            if (bmode_passthrough(BMODE)) st_unit<ST, NW>(pgx, gr);
+            else st_unit<ST, NW>(pgx, pack_unit<T, NW>(fg));
+            pgx += sb;
+        }
+        accS += (double)ls; accB += (double)lb;
+        px += sb; pg += sb;
+    }
+    if (!bmode_reduces(BMODE)) {                  // eval: parameters get exact zeros (lsq_kernel.h:143-144)
+        if (blockIdx.x == 0 && threadIdx.x == 0) { store_param(sg.gscale, 0, sg.pdt, 0.0); store_param(sg.gshift, 0, sg.pdt, 0.0); }
+        return;
+    }
+    TileCtx tl;
+    tl.c = 0; tl.ltile = blockIdx.x; tl.j = (int)blockIdx.x; tl.pidx = 0;
+    if (!channel_finish<THREADS, THREADS>(sg, tl, accS, accB, red, &last_flag, threadIdx.x)) return;
+    if (threadIdx.x == 0) {
+        store_param(sg.gscale, 0, sg.pdt, accS * sg.gs);
+        store_param(sg.gshift, 0, sg.pdt, sg.sym ? 0.0 : accB * sg.gs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Observer step (init_mode='observer', observers.py:446-449): ONE read of x gives the per-tensor /
 // per-channel min and max; the last tile of a channel then does, on the device and with the same
 // fp32 operations in the same order, what torch's observers and the module do on the host:

@@ -89,6 +89,10 @@ inline KernelFn get_bwd_kernel(int xdtype, int mode, int nw, int bmode, int grou
     return get_bwd_kernel_bf16(mode, nw, bmode, group);
 }
 KernelFn get_stats_kernel(int xdtype, int nw, int group);
+// kern_flat.cu: lean per-tensor kernels for single launches (M_FP32 arithmetic only); the descriptor is their one parameter
+using FlatKernelFn = void (*)(const Seg);
+FlatKernelFn get_flatfwd_kernel(int xdtype, bool init);
+FlatKernelFn get_flatbwd_kernel(int xdtype, int bmode);
 // kern_rows.cu: lean warp-per-row forward / backward for aligned weight rows (M_FP32 arithmetic only)
 KernelFn get_rowfwd_kernel(int xdtype, bool init);
 KernelFn get_rowbwd_kernel(int xdtype, int bmode);
@@ -141,7 +145,13 @@ struct Tuning {
     int whole_waves = 1;        // round big-tensor tile counts to whole waves of resident CTAs
     int pdl = 1;                // launch with programmatic stream serialization (prologue overlaps predecessor's tail)
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
- int rowkernels = 1;         // forward / backward over aligned weight rows: the lean warp-per-row kernels (0: the general warp-group kernels)
+    // single per-tensor launches in 32-byte aligned buffers: the lean kernels (bit-identical results).  1 = forward only (default),
+    // 2 = forward and backward, 0 = off.  B200, bf16 sites: lean forward is faster alone (ncu: 120.7 vs 123.5 us on the largest
+    // site, 8.5 vs 10.0 on the smallest) and in a stream (123.6 vs 127.0); lean backward is faster alone (186.4 vs 190.7) but
+    // SLOWER back to back under programmatic dependent launch (193.6 vs 188.0 per launch) - the general kernel's long set-up
+    // runs before its griddepcontrol.wait and overlaps the predecessor's reduction tail - so the backward stays general
+    int flatkernels = 1;
+    int rowkernels = 1;         // forward / backward over aligned weight rows: the lean warp-per-row kernels (0: the general warp-group kernels)
     int rowstats = 2;           // mu +- 3 sigma over aligned weight rows: the lean warp-per-row kernel, variant 1 / 2 / 3 (kern_stats.cu); 0: the general kernel
                                 // 54 ResNet-50 weights under ncu on B200: general kernel 34.5 us, variant 1 28.7, 2 25.2, 3 26.3
     // resident CTAs/SM the kernel family really gets (its __launch_bounds__): whole-wave rounding uses these.  The two-operand
@@ -168,6 +178,10 @@ struct Geometry {
 };
 
 inline int elem_size(int dt) { return dt == DT_F64 ? 8 : (dt == DT_F32 ? 4 : 2); }
+// one contiguous channel streamed by CTA groups with interleaved (or single) splits, 32-byte aligned buffers: the lean per-tensor kernels apply
+inline bool flat_eligible(const Geometry& g, int xdtype) {
+    return g.regime == 0 && g.C == 1 && g.nw == 8 && g.group != 32 && (g.splits == 1 || g.interleave) && xdtype != DT_F64 && g.inner > 0;
+}
 // contiguous channel rows that one warp owns, in tensors whose base pointers are 32-byte aligned: the lean row kernels apply
 inline bool rowstats_eligible(const Geometry& g, int xdtype) {
     return g.regime == 0 && g.group == 32 && g.nw == 8 && g.splits == 1 && xdtype != DT_F64 && g.inner > 0;   // rows need not be 32-byte multiples: scalar head / tail

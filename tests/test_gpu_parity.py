@@ -449,3 +449,59 @@ def test_large_bf16_site_properties():
     xfq = torch.clamp(v, 0, 127).round() * 0.03
     terms = torch.where(inside, gf * (xfq - xf) / 0.03, torch.where(v <= 0, gf * 0, gf * 127))
     assert abs(gs_s.item() - terms.sum().item()) <= 1e-4 * terms.abs().sum().item()
+
+
+# ------------------------------------------------------------------------------------------------
+# lean kernels (per-tensor single launches, weight rows) against the general kernels they shortcut
+# ------------------------------------------------------------------------------------------------
+def _with_tuning(lib, spec, fn):
+    assert lib.lsqb200_set_tuning(spec.encode()) == 0
+    try:
+        return fn()
+    finally:
+        lib.lsqb200_set_tuning(b"")
+
+
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("n", [300_001, (1 << 20) + 3, 6_422_528, 51_380_224])
+@pytest.mark.parametrize("mode", ["normal", "init", "eval"])
+def test_lean_per_tensor_kernels_bit_identical_to_general(dt, n, mode, native_lib):
+    """lsq_flatfwd / lsq_flatbwd keep the general kernels' tiles, unit <-> thread mapping and fixed-order reduction: every
+    output, the parameter gradients included, is the same bit pattern."""
+    x, g = _mk(n, DT[dt], seed=n % 997)
+    s, b = _params([0.03], [-1.7])
+    q = U.qa(init_mode=(mode == "init"), eval_mode=(mode == "eval"))
+
+    def run():
+        y = U.fwd(x, s, b, q)
+        gx, gs, gb = U.bwd(g, x, s, b, q)
+        torch.cuda.synchronize()
+        return y, gx, gs, gb
+    lean = _with_tuning(native_lib, "flatkernels=2", run)
+    general = _with_tuning(native_lib, "flatkernels=0", run)
+    for a_, b_ in zip(lean, general):
+        assert torch.equal(a_.view(torch.int32 if a_.dtype == torch.float32 else torch.int16),
+                           b_.view(torch.int32 if b_.dtype == torch.float32 else torch.int16))
+    assert U.same_bits(lean[0], U.oracle_fwd(x, s, b, q))
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+@pytest.mark.parametrize("shape", [(512, 512, 3, 3), (64, 3, 7, 7), (1000, 2048), (33, 1, 5, 5)])
+def test_lean_weight_row_kernels_match_general(dt, shape, native_lib):
+    n = int(np.prod(shape))
+    x, g = _mk(n, DT[dt], seed=n % 991, scale=0.6)
+    outer, C, inner = geometry(shape, 0)
+    gen = torch.Generator().manual_seed(C)
+    s = (0.02 + 0.02 * torch.rand(C, generator=gen)).to(U.DEV)
+    b = (-torch.rand(C, generator=gen)).to(U.DEV)
+    q = U.qa()
+
+    def run():
+        y = U.fwd(x, s, b, q, outer, C, inner, True)
+        gx, gs, gb = U.bwd(g, x, s, b, q, outer, C, inner, True)
+        torch.cuda.synchronize()
+        return y, gx, gs, gb
+    lean = _with_tuning(native_lib, "rowkernels=1", run)
+    general = _with_tuning(native_lib, "rowkernels=0", run)
+    assert torch.equal(lean[0], general[0]) and torch.equal(lean[1], general[1])
+    assert torch.allclose(lean[2], general[2], rtol=1e-6, atol=1e-12) and torch.allclose(lean[3], general[3], rtol=1e-6, atol=1e-12)
