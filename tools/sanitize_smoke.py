@@ -70,4 +70,43 @@ for shp in ((16, 3, 7, 7), (32, 16, 1, 1), (8, 8, 3, 3)):
 plan = LSQPlan(sites); plan.forward(); plan.backward(); out = plan.weight_init_stats()
 torch.cuda.synchronize()
 assert torch.isfinite(out).all()
+# fused prologues (relu / add+relu / add): row-tiled (per-tensor, per-channel long rows, warp-group rows) and column-layout kernels
+def check_pre(code, x, x2, g, s, b, q, outer=1, C=1, inner=None, pc=False):
+    relu = code != _cabi.PRE_ADD
+    y = U.fwd(x, s, b, q, outer, C, inner, pc, prologue=code, x2=x2)
+    assert U.same_bits(y, U.oracle_fwd(x, s, b, q, outer, C, inner, pc, relu=relu, x2=x2))
+    gx, gs, gb = U.bwd(g, x, s, b, q, outer, C, inner, pc, prologue=code, x2=x2)
+    ogx, ogs, ogb, ms, mb = U.oracle_bwd(g, x, s, b, q, outer, C, inner, pc, relu=relu, x2=x2)
+    assert U.same_bits(gx, ogx)
+    U.assert_grads_close(gs, ogs, ms, 1e-5); U.assert_grads_close(gb, ogb, mb, 1e-5)
+for code in (_cabi.PRE_RELU, _cabi.PRE_ADD_RELU, _cabi.PRE_ADD):
+    for dt in (torch.float32, torch.bfloat16):
+        for n in (5, 4099, 300_001):
+            x = torch.randn(n, generator=gen).to(dt).to(U.DEV); g = torch.randn(n, generator=gen).to(dt).to(U.DEV)
+            x2 = torch.randn(n, generator=gen).to(dt).to(U.DEV) if code != _cabi.PRE_RELU else None
+            for mode in (dict(), dict(init_mode=True)):
+                check_pre(code, x, x2, g, torch.tensor([0.03], device=U.DEV), torch.tensor([-1.7], device=U.DEV), U.qa(**mode))
+        for shape, axis in (((64, 3, 7, 7), 0), ((4, 32, 14, 14), 1), ((2, 16, 56, 56), 1), ((16, 64, 7, 7), 1)):
+            n = int(np.prod(shape)); outer = int(np.prod(shape[:axis])); C = shape[axis]; inner = n // (outer * C)
+            x = torch.randn(n, generator=gen).to(dt).to(U.DEV); g = torch.randn(n, generator=gen).to(dt).to(U.DEV)
+            x2 = torch.randn(n, generator=gen).to(dt).to(U.DEV) if code != _cabi.PRE_RELU else None
+            s = (0.02 + 0.02 * torch.rand(C, generator=gen)).to(U.DEV); b = (-torch.rand(C, generator=gen)).to(U.DEV)
+            check_pre(code, x, x2, g, s, b, U.qa(), outer, C, inner, True)
+# lean kernels against the general ones: flat per-tensor (incl. the backward twin behind the knob), weight rows with head / tail, row statistics
+for spec in (b"flatkernels=2", b"flatkernels=0,rowkernels=0,rowstats=0", b""):
+    assert lib.lsqb200_set_tuning(spec) == 0
+    for dt in (torch.float32, torch.bfloat16):
+        for n in (37, 4099 * 8, 300_001):
+            x = torch.randn(n, generator=gen).to(dt).to(U.DEV); g = torch.randn(n, generator=gen).to(dt).to(U.DEV)
+            check(x, g, torch.tensor([0.03], device=U.DEV), torch.tensor([-1.7], device=U.DEV), U.qa())
+        for shape in ((64, 3, 7, 7), (33, 1, 5, 5), (48, 64, 3, 3), (7, 1)):
+            n = int(np.prod(shape)); C = shape[0]
+            x = torch.randn(n, generator=gen).to(dt).to(U.DEV); g = torch.randn(n, generator=gen).to(dt).to(U.DEV)
+            s = (0.02 + 0.02 * torch.rand(C, generator=gen)).to(U.DEV); b = (-torch.rand(C, generator=gen)).to(U.DEV)
+            check(x, g, s, b, U.qa(), 1, C, n // C, True)
+            so = torch.empty(C, device=U.DEV)
+            assert lib.lsqb200_weight_init_stats(x.data_ptr(), so.data_ptr(), 1, C, n // C, _cabi.F32 if dt == torch.float32 else _cabi.BF16,
+                                                 -128, 127, U.workspace().data_ptr(), U.workspace().numel(), U.stream()) == 0
+            torch.cuda.synchronize()
+lib.lsqb200_set_tuning(b"")
 print("sanitize_smoke ok")
