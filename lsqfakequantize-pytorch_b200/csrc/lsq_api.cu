@@ -253,7 +253,7 @@ int forward_common(const void* x, const void* x2, void* y, const void* scale, co
     const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
     if (mode == M_FP32 && tuning().flatkernels && flat_eligible(g, xdt))
         return launch_flat(get_flatfwd_kernel(xdt, q->init_mode != 0), seg, g.grid, (cudaStream_t)stream);
-    KernelFn k = (mode == M_FP32 && tuning().rowkernels && rowstats_eligible(g, xdt)) ? get_rowfwd_kernel(xdt, q->init_mode != 0)
+    KernelFn k = (mode == M_FP32 && tuning().rowkernels && row_kernels_eligible(g, xdt)) ? get_rowfwd_kernel(xdt, q->init_mode != 0)
                                                                                       : get_fwd_kernel(xdt, mode, g.nw, q->init_mode != 0, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
@@ -326,7 +326,7 @@ int backward_common(const void* grad, const void* x, const void* x2, void* gx, c
     const Seg seg = make_seg(a, g, partials, counters, 0);
     if (mode == M_FP32 && tuning().flatkernels >= 2 && flat_eligible(g, xdt))
         return launch_flat(get_flatbwd_kernel(xdt, bmode_of(q)), seg, g.grid, st);
-    KernelFn k = (mode == M_FP32 && tuning().rowkernels && rowstats_eligible(g, xdt)) ? get_rowbwd_kernel(xdt, bmode_of(q))
+    KernelFn k = (mode == M_FP32 && tuning().rowkernels && row_kernels_eligible(g, xdt)) ? get_rowbwd_kernel(xdt, bmode_of(q))
                                                                                       : get_bwd_kernel(xdt, mode, g.nw, bmode_of(q), g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, st);
 }
@@ -403,7 +403,7 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         Geometry g = plan_geometry(s.outer, s.C, s.inner, s.xdtype, kind, al, tuning_for_mode(tn, mode));
         int variant = 0;
         KernelFn k = nullptr;
-        const bool lean = mode == M_FP32 && tn.rowkernels && rowstats_eligible(g, s.xdtype);   // aligned weight rows: warp-per-row kernels
+        const bool lean = mode == M_FP32 && tn.rowkernels && row_kernels_eligible(g, s.xdtype);   // aligned weight rows: warp-per-row kernels
         if (kind == K_FWD) {
             variant = s.q.init_mode != 0;
             k = lean ? get_rowfwd_kernel(s.xdtype, variant != 0) : get_fwd_kernel(s.xdtype, mode, g.nw, variant, g.group);
@@ -415,7 +415,7 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         }
         else {
             if (s.xdtype == DT_F64) continue;   // no float64 statistics (the module cannot hold float64 weights): slot left untouched
-            if (rowstats_eligible(g, s.xdtype) && tn.rowstats) { variant = 1; k = get_rowstats_kernel(s.xdtype, tn.rowstats); }
+            if (row_kernels_eligible(g, s.xdtype) && tn.rowstats) { variant = 1; k = get_rowstats_kernel(s.xdtype, tn.rowstats); }
             else k = get_stats_kernel(s.xdtype, g.nw, g.group);
         }
         if (!k) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
@@ -622,7 +622,7 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
                          C > 1, &q);
     a.stats_out = scale_out;
     const Seg seg = make_seg(a, g, partials, counters, 0);
-    KernelFn k = (rowstats_eligible(g, xdtype) && tuning().rowstats) ? get_rowstats_kernel(xdtype, tuning().rowstats) : get_stats_kernel(xdtype, g.nw, g.group);
+    KernelFn k = (row_kernels_eligible(g, xdtype) && tuning().rowstats) ? get_rowstats_kernel(xdtype, tuning().rowstats) : get_stats_kernel(xdtype, g.nw, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }
 

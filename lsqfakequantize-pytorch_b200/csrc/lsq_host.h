@@ -183,7 +183,7 @@ inline bool flat_eligible(const Geometry& g, int xdtype) {
     return g.regime == 0 && g.C == 1 && g.nw == 8 && g.group != 32 && (g.splits == 1 || g.interleave) && xdtype != DT_F64 && g.inner > 0;
 }
 // contiguous channel rows that one warp owns, in tensors whose base pointers are 32-byte aligned: the lean row kernels apply
-inline bool rowstats_eligible(const Geometry& g, int xdtype) {
+inline bool row_kernels_eligible(const Geometry& g, int xdtype) {
     return g.regime == 0 && g.group == 32 && g.nw == 8 && g.splits == 1 && xdtype != DT_F64 && g.inner > 0;   // rows need not be 32-byte multiples: scalar head / tail
 }
 
