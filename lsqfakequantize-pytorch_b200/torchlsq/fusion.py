@@ -83,6 +83,8 @@ def unfuse_prologues(model: torch.nn.Module) -> int:
         kind = getattr(mod, _MARK, None)
         if not kind:
             continue
+        if kind == "relu_fx":                    # graph-mode patch: the graph still passes relu=True, only a re-prepare undoes it
+            continue
         if kind == "relu":
             mod.__dict__.pop("forward", None)
             mod.activation_post_process.fuse_relu = False
@@ -92,3 +94,80 @@ def unfuse_prologues(model: torch.nn.Module) -> int:
         mod.__dict__.pop(_MARK, None)
         n += 1
     return n
+
+
+# ---- FX graph mode (torch.ao.quantization.quantize_fx.prepare_qat_fx) --------------------------------------------------------
+def _is_relu_node(node, modules):
+    import torch.nn.functional as F
+    if node.op == "call_function":
+        return node.target in (torch.relu, F.relu, torch.relu_) and len(node.args) >= 1
+    if node.op == "call_method":
+        return node.target in ("relu", "relu_")
+    if node.op == "call_module":
+        return type(modules.get(node.target)) is torch.nn.ReLU
+    return False
+
+
+def _is_add_node(node):
+    import operator
+    if node.op == "call_function" and node.target in (operator.add, operator.iadd, torch.add):
+        ok = len(node.args) == 2 and not node.kwargs          # torch.add(a, b, alpha=...) is left alone
+    elif node.op == "call_method" and node.target in ("add", "add_"):
+        ok = len(node.args) == 2 and not node.kwargs
+    else:
+        return False
+    return ok and all(isinstance(a, torch.fx.Node) for a in node.args)
+
+
+def fuse_prologues_fx(gm: "torch.fx.GraphModule", relu: bool = True, residual: bool = True) -> Dict[str, int]:
+    """`fuse_prologues` for a GraphModule returned by `prepare_qat_fx`.  There the quantizers are graph nodes
+    (`activation_post_process_N`), so the two patterns are rewritten in the graph itself:
+
+        fused ConvBnReLU2d / ConvReLU2d / LinearReLU -> quantizer   the module loses its F.relu (instance patch), quantizer(x, relu=True)
+        [add ->] [relu ->] quantizer                                 quantizer(a, b, relu=True) / quantizer(x, relu=True) / quantizer(a, b, relu=False)
+
+    Only single-user chains are touched (an in-place ReLU or add whose result something else reads stays as it is).  The
+    rewritten graph trains with bit-identical results; `convert_fx` pattern-matches the ORIGINAL graph, so convert a freshly
+    prepared copy loaded with the trained `state_dict()` (module names and parameters are unchanged by this pass)."""
+    modules = dict(gm.named_modules(remove_duplicate=False))   # prepare_qat_fx shares one quantizer between several nodes (pool, relu ...)
+    done = {"relu": 0, "residual": 0}
+    graph = gm.graph
+    for node in list(graph.nodes):
+        if node.op != "call_module" or not isinstance(modules.get(node.target), LSQFakeQuantizer):
+            continue
+        if len(node.args) != 1 or node.kwargs or not isinstance(node.args[0], torch.fx.Node):
+            continue
+        app = modules[node.target]
+        p = node.args[0]
+        if len(p.users) != 1:
+            continue
+        if relu and p.op == "call_module":
+            mod = modules.get(p.target)
+            parent_forward = _relu_parent_forward(mod) if mod is not None else None
+            if parent_forward is not None and not getattr(mod, _MARK, None):
+                mod.forward = types.MethodType(parent_forward, mod)      # the module without its F.relu ...
+                node.kwargs = {"relu": True}                             # ... which this CALL of the (possibly shared) quantizer applies
+                object.__setattr__(mod, _MARK, "relu_fx")
+                done["relu"] += 1
+                continue
+        has_relu = _is_relu_node(p, modules)
+        src = p.args[0] if has_relu and p.args and isinstance(p.args[0], torch.fx.Node) else None
+        if has_relu and (src is None or len(src.users) != 1):
+            continue                                       # an in-place ReLU on a tensor something else reads: leave it
+        q = src if has_relu else p
+        if residual and _is_add_node(q) and len(q.users) == 1:
+            a, b = q.args
+            node.args = (a, b)
+            node.kwargs = {"relu": bool(has_relu)}
+            if has_relu:
+                graph.erase_node(p)
+            graph.erase_node(q)
+            done["residual"] += 1
+        elif relu and has_relu:
+            node.args = (src,)
+            node.kwargs = {"relu": True}
+            graph.erase_node(p)
+            done["relu"] += 1
+    graph.lint()
+    gm.recompile()
+    return done

@@ -414,8 +414,11 @@ class LSQFakeQuantizer(ObserverBase):
         return (scale, shift, zero_point) if need_shift else (scale, zero_point)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x):
-        return self._run(x, None, self.fuse_relu)
+    def forward(self, x, x2=None, relu=None):
+        """`module(x)` as in the reference.  The two optional arguments (new) are how graph rewrites hand the module the
+        ops in front of it: `module(a, b)` stands for `module(a + b)`, `relu=True` for a ReLU in between (`relu=None`: the
+        module's own `fuse_relu`).  See `forward_add` and `torchlsq.fusion`."""
+        return self._run(x, x2, self.fuse_relu if relu is None else bool(relu))
 
     def forward_add(self, a, b, relu=True):
         """(new, not in the reference) The module applied to `relu(a + b)` (or `a + b`): what

@@ -106,3 +106,71 @@ def test_fused_prologues_train_like_the_unfused_model(init_mode):
     assert "forward" not in fused.b1.conv1.__dict__ and "add_relu" not in fused.b1.skip.__dict__ and not q.fuse_relu
     with torch.no_grad():
         assert torch.allclose(plain(data[1][0]), fused(data[1][0]), rtol=1e-5, atol=1e-6)
+
+
+def test_fx_graph_mode_fusion_trains_like_the_unfused_graph():
+    """`fuse_prologues_fx` on a `prepare_qat_fx` GraphModule (the reference's quantizer works in FX graph mode as well): ConvBnReLU2d,
+    add -> relu and a bare add in front of quantizers, two residual blocks; fused and unfused graphs train side by side with
+    bit-identical logits and loss."""
+    import torch.ao.quantization as tq
+    from torch.ao.quantization import QConfigMapping
+    from torch.ao.quantization.quantize_fx import prepare_qat_fx
+    from torchlsq import LSQFakeQuantizer
+    from torchlsq.fusion import fuse_prologues_fx
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+
+    class Block(nn.Module):
+        def __init__(self, c):
+            super().__init__()
+            self.conv1, self.bn1, self.relu1 = nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c), nn.ReLU()
+            self.conv2, self.bn2 = nn.Conv2d(c, c, 3, padding=1, bias=False), nn.BatchNorm2d(c)
+
+        def forward(self, x):
+            y = self.relu1(self.bn1(self.conv1(x)))
+            y = self.bn2(self.conv2(y))
+            return torch.relu(y + x)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.stem, self.stem_bn, self.stem_relu = nn.Conv2d(3, 16, 3, padding=1, bias=False), nn.BatchNorm2d(16), nn.ReLU()
+            self.b1, self.b2 = Block(16), Block(16)
+            self.fc = nn.Linear(16, 10)
+
+        def forward(self, x):
+            x = self.stem_relu(self.stem_bn(self.stem(x)))
+            a = self.b1(x)
+            b = self.b2(a)
+            return self.fc((a + b).mean((2, 3)))
+
+    def build():
+        torch.manual_seed(0)
+        act = LSQFakeQuantizer.with_args(observer=tq.MovingAverageMinMaxObserver, otype="activation", init_mode="observer", init_batches=2)
+        wei = LSQFakeQuantizer.with_args(observer=None, otype="weight", dtype=torch.qint8, qscheme=torch.per_channel_symmetric,
+                                         init_mode="learnable", avoid_torch_overflow=False)
+        gm = prepare_qat_fx(Net().train(), QConfigMapping().set_global(tq.QConfig(activation=act, weight=wei)),
+                            example_inputs=(torch.randn(1, 3, 16, 16),))
+        return gm.to(DEV)
+
+    plain, fused = build(), build()
+    done = fuse_prologues_fx(fused)
+    assert done["relu"] >= 3 and done["residual"] >= 3, done
+    gen = torch.Generator().manual_seed(1)
+    data = [(torch.randn(16, 3, 16, 16, generator=gen).to(DEV), torch.randint(0, 10, (16,), generator=gen).to(DEV)) for _ in range(7)]
+    opts = None
+    for step, (x, t) in enumerate(data):
+        outs = []
+        for i, net in enumerate((plain, fused)):
+            logits = net(x)
+            loss = F.cross_entropy(logits, t)
+            outs.append((logits.detach().clone(), loss.detach().clone()))
+            if opts is not None:
+                opts[i].zero_grad()
+                loss.backward()
+                opts[i].step()
+        if opts is None:
+            opts = [torch.optim.SGD(n.parameters(), lr=0.02, momentum=0.9) for n in (plain, fused)]
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]), step
+    for (n0, p0), (n1, p1) in zip(plain.named_parameters(), fused.named_parameters()):
+        assert n0 == n1 and torch.allclose(p0, p1, rtol=1e-5, atol=1e-7), n0

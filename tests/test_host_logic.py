@@ -304,3 +304,44 @@ def test_fuse_prologues_patches_instances_only():
     assert unfuse_prologues(m) == 3
     assert "forward" not in m.conv1.__dict__ and "add_relu" not in m.skip.__dict__ and not m.conv1.activation_post_process.fuse_relu
     assert fuse_prologues(m, relu=False) == {"relu": 0, "residual": 1}
+
+
+def test_fuse_prologues_fx_rewrites_single_user_chains_only():
+    import torch.ao.quantization as tq
+    import torch.nn as nn
+    from torch.ao.quantization import QConfigMapping
+    from torch.ao.quantization.quantize_fx import prepare_qat_fx
+    from torchlsq.fusion import fuse_prologues_fx
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1, self.bn1, self.relu1 = nn.Conv2d(8, 8, 3, padding=1, bias=False), nn.BatchNorm2d(8), nn.ReLU()
+            self.conv2, self.bn2 = nn.Conv2d(8, 8, 3, padding=1, bias=False), nn.BatchNorm2d(8)
+            self.pool, self.relu2 = nn.AdaptiveAvgPool2d(1), nn.ReLU(inplace=True)
+
+        def forward(self, x):
+            y = self.relu1(self.bn1(self.conv1(x)))
+            y = self.bn2(self.conv2(y))
+            z = torch.relu(y + x)                       # add -> relu -> quantizer: one call
+            w = self.relu2(self.pool(z))                # relu behind a quantizer torch shares between pool and relu: per-call flag
+            t = y + w                                   # `y` has a second user (the add above): this add is still single-user, fused
+            return z + t
+
+    qc = tq.QConfig(activation=LSQFakeQuantizer.with_args(observer=tq.MovingAverageMinMaxObserver, otype='activation'),
+                    weight=LSQFakeQuantizer.with_args(observer=None, otype='weight', dtype=torch.qint8,
+                                                      qscheme=torch.per_channel_symmetric, init_mode='learnable'))
+    gm = prepare_qat_fx(Block().train(), QConfigMapping().set_global(qc), example_inputs=(torch.randn(1, 8, 8, 8),))
+    before = {n.name for n in gm.graph.nodes}
+    done = fuse_prologues_fx(gm)
+    after = {n.name: n for n in gm.graph.nodes}
+    assert done["relu"] == 2 and done["residual"] == 3
+    assert not any("relu" in n or n.startswith("add") for n in after)          # every relu / add node is gone ...
+    assert {n for n in before if "relu" in n or n.startswith("add")}           # ... and there were some
+    calls = [n for n in gm.graph.nodes if n.op == "call_module" and n.kwargs]
+    assert sorted((len(n.args), n.kwargs["relu"]) for n in calls) == [(1, True), (1, True), (2, False), (2, False), (2, True)]
+    modules = dict(gm.named_modules(remove_duplicate=False))
+    assert all(isinstance(modules[n.target], LSQFakeQuantizer) for n in calls)
+    assert not any(m.fuse_relu for m in modules.values() if isinstance(m, LSQFakeQuantizer))   # graph mode keeps the flag per call
+    assert "forward" in gm.conv1.__dict__                                       # ConvBnReLU2d lost its F.relu
+    assert fuse_prologues_fx(gm) == {"relu": 0, "residual": 0}
