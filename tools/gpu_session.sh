@@ -17,7 +17,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:ls
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-plan-mode --no-fusion-mode > $out/${tag}_launches.log 2>&1
 ncu --set full --clock-control none --import-source on --kernel-name regex:lsq_bwd_kernel --launch-skip 69 --launch-count 2 \
     -f -o $out/${tag}_prof_bwd python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-plan-mode --no-fusion-mode > $out/${tag}_prof_bwd.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name regex:lsq_fwd_kernel --launch-skip 1 --launch-count 1 \
+ncu --set full --clock-control none --import-source on --kernel-name regex:lsq_flatfwd_kernel --launch-skip 1 --launch-count 1 \
     -f -o $out/${tag}_prof_fwd python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-plan-mode --no-fusion-mode > $out/${tag}_prof_fwd.log 2>&1
 python bench.py > $out/${tag}_bench.json 2>$out/${tag}_bench.err
 tail -n 3 $out/${tag}_ab_*.json $out/${tag}_bench.json
