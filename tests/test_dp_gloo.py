@@ -22,14 +22,31 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _site_grads(x, g, scale, shift, per_channel, cfg_kw):
+def _site_grads(x, g, scale, shift, per_channel, cfg_kw, x2=None, relu=False):
+    """x2 / relu: the site sits behind a fused prologue (residual add and / or ReLU) - sharding by batch and the
+    flat-buffer all-reduce are the same, the per-rank gradients are those of fake_quant(relu(x + x2))."""
     from oracle import lsq_oracle as O
     if per_channel:
         outer, C, inner = 1, x.shape[0], int(np.prod(x.shape[1:]))
     else:
         outer, C, inner = 1, 1, x.size
-    _, gs, gb = O.backward(g.reshape(-1), x.reshape(-1), scale, shift, O.cfg(**cfg_kw), outer, C, inner, per_channel)
+    if x2 is not None:
+        _, gs, gb = O.backward_add(g.reshape(-1), x.reshape(-1), x2.reshape(-1), scale, shift, O.cfg(**cfg_kw), outer, C, inner,
+                                   per_channel, with_relu=relu)
+    elif relu:
+        _, gs, gb = O.backward_relu(g.reshape(-1), x.reshape(-1), scale, shift, O.cfg(**cfg_kw), outer, C, inner, per_channel)
+    else:
+        _, gs, gb = O.backward(g.reshape(-1), x.reshape(-1), scale, shift, O.cfg(**cfg_kw), outer, C, inner, per_channel)
     return gs, gb
+
+
+def _prologue_of(i, x, lo, hi, fused):
+    """fused runs: site 0 is relu -> fq, site 1 the residual join relu(x + x2) -> fq (x2 derived from x so every process agrees)."""
+    if not fused:
+        return {}
+    if i == 0:
+        return dict(relu=True)
+    return dict(x2=np.ascontiguousarray(np.flip(x, axis=1) * 0.5)[lo:hi], relu=True)
 
 
 def _make_problem():
@@ -45,7 +62,7 @@ ACT_CFG = dict(quant_min=0, quant_max=127, type_min=0, type_max=255)
 W_CFG = dict(quant_min=-128, quant_max=127, type_min=-128, type_max=127, sym=True)
 
 
-def _worker(rank, world, port, average, out_dir):
+def _worker(rank, world, port, average, out_dir, fused=False):
     import sys
     for p in (str(PKG), str(ROOT)):
         if p not in sys.path:
@@ -58,7 +75,7 @@ def _worker(rank, world, port, average, out_dir):
     flat = FlatGradBuffer([("act0", 1), ("act1", 1), ("w0", 6)], "cpu")
     for i, (x, g) in enumerate(acts):
         lo, hi = shard_batch(x.shape[0], rank, world)
-        gs, gb = _site_grads(x[lo:hi], g[lo:hi], [0.05], [-0.7], False, ACT_CFG)
+        gs, gb = _site_grads(x[lo:hi], g[lo:hi], [0.05], [-0.7], False, ACT_CFG, **_prologue_of(i, x, lo, hi, fused))
         s_view, b_view = flat.views(f"act{i}")
         s_view.copy_(torch.from_numpy(gs).float())
         b_view.copy_(torch.from_numpy(gb).float())
@@ -72,15 +89,15 @@ def _worker(rank, world, port, average, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,average", [(2, False), (2, True), (3, False)])
-def test_flat_grad_allreduce_equals_sum_of_shard_grads(tmp_path, world, average):
+@pytest.mark.parametrize("world,average,fused", [(2, False, False), (2, True, False), (3, False, False), (2, False, True)])
+def test_flat_grad_allreduce_equals_sum_of_shard_grads(tmp_path, world, average, fused):
     import sys
     for p in (str(PKG), str(ROOT)):
         if p not in sys.path:
             sys.path.insert(0, p)
     from torchlsq.dp import expected_allreduced, shard_batch
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, average, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, average, str(tmp_path), fused), nprocs=world, join=True)
     got = [torch.load(tmp_path / f"rank{r}.pt") for r in range(world)]
     for r in range(1, world):
         assert torch.equal(got[0], got[r])                    # every rank holds the same reduced buffer
@@ -88,9 +105,9 @@ def test_flat_grad_allreduce_equals_sum_of_shard_grads(tmp_path, world, average)
     per_rank = []
     for r in range(world):
         vals = []
-        for x, g in acts:
+        for i, (x, g) in enumerate(acts):
             lo, hi = shard_batch(x.shape[0], r, world)
-            gs, gb = _site_grads(x[lo:hi], g[lo:hi], [0.05], [-0.7], False, ACT_CFG)
+            gs, gb = _site_grads(x[lo:hi], g[lo:hi], [0.05], [-0.7], False, ACT_CFG, **_prologue_of(i, x, lo, hi, fused))
             vals += [gs, gb]
         gs, gb = _site_grads(w, gw[r], [0.002] * 6, [0.0] * 6, True, W_CFG)
         vals += [gs, gb]
@@ -99,7 +116,7 @@ def test_flat_grad_allreduce_equals_sum_of_shard_grads(tmp_path, world, average)
     assert torch.allclose(got[0].double(), want, rtol=1e-6, atol=1e-9)
     # local-numel scaling: the sharded sum is NOT the unsharded gradient (it is larger by ~sqrt(world))
     x, g = acts[0]
-    full, _ = _site_grads(x, g, [0.05], [-0.7], False, ACT_CFG)
+    full, _ = _site_grads(x, g, [0.05], [-0.7], False, ACT_CFG, **_prologue_of(0, x, 0, x.shape[0], fused))
     ratio = float(want[0]) * (world if average else 1) / float(full[0])
     assert abs(ratio - np.sqrt(world)) < 0.2 * np.sqrt(world)
 
