@@ -309,6 +309,8 @@ def run_b200(args):
         aplan = LSQPlan(asites)
         launches_per_step = aplan.launches(False) + aplan.launches(True) + wplan.launches(False) + wplan.launches(True)
 
+    pending = [None]      # handle of the flat-grad all-reduce in flight on the side stream (N > 1)
+
     def step(ev0=None, ev1=None):
         if aplan is not None:
             aplan.forward()
@@ -316,6 +318,9 @@ def run_b200(args):
             for c in fwd_calls:
                 fwd_t(*c)
         wplan.forward()
+        if pending[0] is not None:      # the previous step's all-reduce still reads the flat buffer the backward overwrites
+            pending[0].wait()
+            pending[0] = None
         if ev0 is not None:
             ev0.record(stream)
         if aplan is not None:
@@ -327,7 +332,14 @@ def run_b200(args):
             ev1.record(stream)
         wplan.backward()
         if world > 1:
-            flat.all_reduce()
+            # side stream: the collective waits for this step's backward and overlaps the next step's forward
+            # (DESIGN.md section 5); the compute stream only joins it again in front of the next backward
+            pending[0] = flat.all_reduce(side_stream=not args.inline_allreduce)
+
+    def drain():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
 
     n_act = sum(a["n"] for a in acts)
     n_w = sum(math.prod(s) for s in W_SHAPES)
@@ -342,27 +354,13 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    # sanity: the C ABI must have really run (outputs finite, grads written)
-    assert torch.isfinite(flat.flat).all().item() and flat.flat.abs().sum().item() > 0
+    drain()
+    torch.cuda.synchronize()
+    # sanity: the C ABI must have really run (outputs finite, grads written); recorded, never a reason to lose the line
+    ran_ok = bool(torch.isfinite(flat.flat).all().item() and flat.flat.abs().sum().item() > 0)
     dp_check = None
     if world > 1:
-        # data-parallel semantics on the real NCCL path: all-reduced buffer == sum over ranks of the local grads
-        # (each rank scaled with its LOCAL numel), checked on every rank
-        from torchlsq.dp import expected_allreduced
-        for c in fwd_calls:
-            fwd_t(*c)
-        wplan.forward()
-        for c in bwd_calls:
-            bwd_t(*c)
-        wplan.backward()
-        local = flat.flat.clone()
-        gathered = [torch.empty_like(local) for _ in range(world)]
-        dist.all_gather(gathered, local)
-        flat.all_reduce()
-        want = expected_allreduced(gathered)
-        err = ((flat.flat.double() - want).abs() / (want.abs() + 1e-12)).max().item()
-        assert err < 1e-6, f"all-reduced scale/shift grads differ from the sum of the shards' grads: {err}"
-        dp_check = {"max_rel_err_vs_sum_of_shard_grads": err, "floats": flat.numel}
+        dp_check = run_dp_check(torch, dist, flat, world, fwd_calls, bwd_calls, fwd_t, bwd_t, wplan)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     bw = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
@@ -370,6 +368,7 @@ def run_b200(args):
         e0.record(stream)
         for k in range(args.steps):
             step(*bw[k])
+        drain()                     # the last step's all-reduce belongs to the timed region
         e1.record(stream)
         barrier()
     ms_total = e0.elapsed_time(e1)
@@ -393,16 +392,20 @@ def run_b200(args):
         p2 = LSQPlan(asites)
 
         def step2():
-            p2.forward(); wplan.forward(); p2.backward(); wplan.backward()
+            p2.forward(); wplan.forward()
+            drain()
+            p2.backward(); wplan.backward()
             if world > 1:
-                flat.all_reduce()
+                pending[0] = flat.all_reduce(side_stream=not args.inline_allreduce)
         for _ in range(3):
             step2()
+        drain()
         barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record(stream)
         for _ in range(args.steps):
             step2()
+        drain()
         p1.record(stream)
         barrier()
         tp = torch.tensor([p0.elapsed_time(p1)], device=dev, dtype=torch.float64)
@@ -433,6 +436,15 @@ def run_b200(args):
     i1.record(stream)
     torch.cuda.synchronize()
     init_gbps = 4 * n_w / (i0.elapsed_time(i1) / 10 * 1e-3) / 1e9
+
+    # ---- the same step through the PUBLIC API on device-resident tensors (the drop-in a user calls): functional op +
+    #      autograd, and LSQFakeQuantizer modules
+    api_mode = None
+    if world == 1 and not args.no_api_mode:
+        try:
+            api_mode = run_api_mode(args, torch, acts, wsites, stream, ms_step)
+        except Exception as exc:       # a report, never a reason to lose the line
+            api_mode = {"error": repr(exc)}
 
     # ---- end to end through the public op with HOST buffers (pinned), copies inside the timed region
     e2e = None
@@ -482,7 +494,9 @@ def run_b200(args):
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": bwd_bytes, "avg_ms_per_step": round(bwd_ms, 4)},
-            "plan_mode": plan_mode, "prologue_fusion": fusion_mode, "weight_init_stats_GBps": round(init_gbps, 1), "dp_check": dp_check,
+            "api_mode": api_mode, "plan_mode": plan_mode, "prologue_fusion": fusion_mode, "weight_init_stats_GBps": round(init_gbps, 1), "dp_check": dp_check, "kernels_ran": ran_ok,
+            "allreduce": (None if world == 1 else ("inline on the compute stream" if args.inline_allreduce else
+                                                   "side stream, overlapped with the next step's forward; joined in front of the next backward and before the final event")),
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "clocks": clk.summary(),
         }
@@ -491,6 +505,41 @@ def run_b200(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_dp_check(torch, dist, flat, world, fwd_calls, bwd_calls, fwd_t, bwd_t, wplan):
+    """Data-parallel semantics on the real NCCL path: the all-reduced flat buffer equals the sum over ranks of the
+    local grad_scale / grad_shift (each rank scaled with its LOCAL numel as the reference op would be under DDP,
+    /root/reference/torchlsq/csrc/ops/cuda/lsq_cuda.cu:124,274).
+
+    Bound per element: an fp32 sum of W addends in any order is within (W-1) * 2^-24 * sum_r |shard_r| of the exact sum
+    (relative to the result it is unbounded once the shards cancel), so
+        |got - want| <= 1e-6 * |want| + W * 2^-24 * sum_r |shard_r|.
+    The outcome is RECORDED (`ok`); it never aborts the bench.  tests/test_gpu_dp_nccl.py is the correctness evidence."""
+    try:
+        for c in fwd_calls:
+            fwd_t(*c)
+        wplan.forward()
+        for c in bwd_calls:
+            bwd_t(*c)
+        wplan.backward()
+        local = flat.flat.clone()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        flat.all_reduce()
+        torch.cuda.synchronize()
+        stack = torch.stack([t.double() for t in gathered])
+        want = stack.sum(0)
+        bound = 1e-6 * want.abs() + world * 2.0 ** -24 * stack.abs().sum(0)
+        err = (flat.flat.double() - want).abs()
+        ratio = (err / bound.clamp_min(1e-300)).max().item()
+        ok = torch.tensor([1 if (ratio <= 1.0 and bool(torch.isfinite(flat.flat).all().item())) else 0], device=local.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return {"ok": bool(ok.item()), "max_err_over_bound": ratio, "max_abs_err": err.max().item(), "floats": flat.numel,
+                "world": world, "bound": "1e-6*|sum| + W*2^-24*sum_r|shard_r| per element (fp32 sum of W addends)",
+                "semantics": "sum over ranks of local-numel-scaled grads (lsq_cuda.cu:124,274)"}
+    except Exception as exc:            # report, never kill the line
+        return {"ok": False, "error": repr(exc)}
 
 
 # per-image shapes of the sites that sit behind a ReLU / behind the residual add + ReLU of a block (torchvision resnet50)
@@ -569,6 +618,149 @@ def run_fusion_mode(args, torch, lib, acts, flat, ws, sp, stream, wplan, qa, BF1
             "hbm_bytes_removed_per_step": 2 * (5 * n_relu + 6 * n_join),
             "note": "all 71 + 54 sites fwd+bwd; unfused = ATen clamp_min / add + relu_ / threshold_backward passes around the plain "
                     "kernels (as torchvision's resnet50 runs them), fused = lsqb200_*_pre with LSQB200_PRE_RELU / PRE_ADD_RELU"}
+
+
+def run_api_mode(args, torch, acts, wsites, stream, cabi_ms):
+    """The timed step driven the way a user drives it: `torchlsq.functional.lsq` + autograd, and `LSQFakeQuantizer`
+    modules, on the same device-resident tensors as the C-ABI step (reference call path:
+    /root/reference/torchlsq/quantized/modules/observers.py:458-461 -> functional.py:95-97 -> csrc/ops/lsq.cpp:104-134 ->
+    csrc/ops/autograd/lsq_autograd.cpp:16-74).  Sites are issued in network order (weight quantizer, then the activation
+    quantizer behind it), one `torch.autograd.backward` per step, grads dropped (set_to_none) after each step."""
+    from torchlsq import LSQFakeQuantizer
+    from torchlsq.functional import lsq
+    dev = acts[0]["x"].device
+    order = []                                # ("a", i) / ("w", j) in network order
+    wi = 0
+    for i in range(len(acts)):
+        order.append(("a", i))
+        if wi < len(wsites) and i < len(acts) - 1:
+            order.append(("w", wi)); wi += 1
+    assert wi == len(wsites)
+    xs = [a["x"].detach().requires_grad_(True) for a in acts]
+    gs = [a["g"] for a in acts]
+    a_par = [(a["s"].clone().requires_grad_(True), a["b"].clone().requires_grad_(True)) for a in acts]
+    w_x = [st.x.detach().requires_grad_(True) for st in wsites]
+    w_par = [(st.scale.clone().requires_grad_(True), st.shift.clone().requires_grad_(True)) for st in wsites]
+    leaves = xs + w_x + [t for p in a_par + w_par for t in p]
+
+    def fn_step():
+        ys, gg = [], []
+        for kind, i in order:
+            if kind == "a":
+                ys.append(lsq(xs[i], a_par[i][0], a_par[i][1], 0, 127, 0, 255)); gg.append(gs[i])
+            else:
+                ys.append(lsq(w_x[i], w_par[i][0], w_par[i][1], -128, 127, -128, 127, axis=0, is_affine=False, is_perchannel=True))
+                gg.append(wsites[i].grad)
+        torch.autograd.backward(ys, gg)
+        for t in leaves:
+            t.grad = None
+
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a_mod = [LSQFakeQuantizer(None, 'activation', dtype=torch.quint8, qscheme=torch.per_tensor_affine, init_mode='learnable',
+                                  init_batches=0, init_scale=0.03).to(dev) for _ in acts]
+        w_mod = [LSQFakeQuantizer(None, 'weight', dtype=torch.qint8, qscheme=torch.per_channel_symmetric, init_mode='learnable',
+                                  avoid_torch_overflow=False).to(dev) for _ in wsites]
+    for m in a_mod + w_mod:
+        m.train()
+
+    def mod_step():
+        ys, gg = [], []
+        for kind, i in order:
+            if kind == "a":
+                ys.append(a_mod[i](xs[i])); gg.append(gs[i])
+            else:
+                ys.append(w_mod[i](w_x[i])); gg.append(wsites[i].grad)
+        torch.autograd.backward(ys, gg)
+        for t in xs + w_x:
+            t.grad = None
+        for m in a_mod + w_mod:
+            m.scale.grad = None
+            m.shift.grad = None
+
+    for _ in range(2):           # first module call only creates the parameters
+        with torch.no_grad():
+            for kind, i in order:
+                (a_mod[i](xs[i]) if kind == "a" else w_mod[i](w_x[i]))
+
+    # the same with every weight quantizer behind ONE multi-tensor launch per direction (torchlsq.multi): LSQGroup for the
+    # functional API, group_weight_quantizers(model) for modules laid out as prepare_qat leaves them
+    from torchlsq.multi import LSQGroup, group_weight_quantizers
+    w_xp = [torch.nn.Parameter(t.detach()) for t in w_x]
+    fgroup = LSQGroup(w_xp, [p[0] for p in w_par], [p[1] for p in w_par], -128, 127, -128, 127, axis=0, is_affine=False,
+                      is_perchannel=True)
+
+    def fn_group_step():
+        yw = fgroup()
+        ys, gg = [], []
+        for kind, i in order:
+            if kind == "a":
+                ys.append(lsq(xs[i], a_par[i][0], a_par[i][1], 0, 127, 0, 255)); gg.append(gs[i])
+            else:
+                ys.append(yw[i]); gg.append(wsites[i].grad)
+        torch.autograd.backward(ys, gg)
+        for t in leaves + w_xp:
+            t.grad = None
+
+    class QatLayer(torch.nn.Module):          # what torch.ao.nn.qat.Conv2d / Linear hold: .weight and .weight_fake_quant
+        def __init__(self, w, q):
+            super().__init__()
+            self.weight, self.weight_fake_quant = w, q
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = torch.nn.ModuleList([QatLayer(w, q) for w, q in zip(w_xp, w_mod)])
+            self.acts = torch.nn.ModuleList(a_mod)
+
+        def forward(self, inputs):
+            ys = []
+            for kind, i in order:
+                if kind == "a":
+                    ys.append(self.acts[i](inputs[i]))
+                else:
+                    layer = self.layers[i]
+                    ys.append(layer.weight_fake_quant(layer.weight))
+            return ys
+    net = Net().train()
+    group_weight_quantizers(net)
+    gg_net = [gs[i] if kind == "a" else wsites[i].grad for kind, i in order]
+
+    def mod_group_step():
+        torch.autograd.backward(net(xs), gg_net)
+        for t in xs + w_xp:
+            t.grad = None
+        for m in a_mod + w_mod:
+            m.scale.grad = None
+            m.shift.grad = None
+
+    out = {}
+    n_sites = len(order)
+    steps = max(3, min(args.steps, 10))
+    for name, fn in (("functional", fn_step), ("module", mod_step), ("functional_weights_grouped", fn_group_step),
+                     ("module_weights_grouped", mod_group_step)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host = 0.0
+        e0.record(stream)
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            fn()
+            host += time.perf_counter() - t0
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_per_step": round(ms, 4), "vs_cabi_step": round(ms / cabi_ms, 4),
+                     "host_ms_per_step": round(host / steps * 1e3, 4), "host_us_per_site": round(host / steps / n_sites * 1e6, 2)}
+    out["sites"] = n_sites
+    out["note"] = ("same 71 + 54 sites and device buffers as `value`; functional = torchlsq.functional.lsq + one torch.autograd.backward "
+                   "per step; module = LSQFakeQuantizer.forward per site (steady state, parameters learning); *_weights_grouped = the 54 weight "
+                   "quantizers behind one autograd node and one launch per direction (torchlsq.multi.LSQGroup / group_weight_quantizers); host_us_per_site = "
+                   "host issue time of a whole fwd+bwd step / sites (the GPU runs behind it)")
+    return out
 
 
 def run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites):
@@ -690,6 +882,8 @@ def main():
     ap.add_argument("--no-plan-mode", action="store_true", help="skip the extra multi-tensor-plan measurement")
     ap.add_argument("--plan-activations", action="store_true", help="run all activation sites through one multi-tensor plan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-api-mode", action="store_true", help="skip the public-API (functional op / module) measurement")
+    ap.add_argument("--inline-allreduce", action="store_true", help="N>1: all-reduce on the compute stream instead of the side stream")
     ap.add_argument("--no-fusion-mode", action="store_true", help="skip the workload-level prologue-fusion measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define LSQB200_ABI_VERSION 2   /* 2: lsqb200_segment gained `prologue` (was reserved) and a trailing `x2`; lsqb200_*_pre entry points */
+#define LSQB200_ABI_VERSION 3   /* 2: lsqb200_segment gained `prologue` (was reserved) and a trailing `x2`; lsqb200_*_pre entry points
+                                 * 3: lsqb200_plan_rebind */
 
 #if defined(__GNUC__)
 #define LSQB200_API __attribute__((visibility("default")))
@@ -232,6 +233,13 @@ typedef struct lsqb200_plan lsqb200_plan; /* opaque */
  * and synchronises; the run calls below do neither).  All segments must share xdtype/pdtype
  * alignment class; mixed dtypes are allowed. */
 LSQB200_API int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan** out);
+/* Re-point the per-step tensors of every segment - outputs that are allocated afresh each training step (y, gx, the
+ * parameter gradients) and the upstream gradient autograd hands over - while x, scale, shift and the layout stay as created.
+ * Each argument is an array of `nseg` device pointers (plan_create's segment order) or NULL to keep the current ones; a new
+ * pointer must be at least as aligned (up to 32 bytes) as the one it replaces.  The device-side table is patched by a tiny
+ * kernel on `stream` (no allocation, no synchronisation, no host staging): use the plan on that one stream. */
+LSQB200_API int lsqb200_plan_rebind(lsqb200_plan* plan, void* const* y, const void* const* grad, void* const* gx,
+                        void* const* gscale, void* const* gshift, void* stream);
 LSQB200_API int lsqb200_plan_forward(lsqb200_plan* plan, void* stream);
 LSQB200_API int lsqb200_plan_backward(lsqb200_plan* plan, void* stream);
 /* float scale_out per channel written to each segment's `gscale` slot is NOT used here:

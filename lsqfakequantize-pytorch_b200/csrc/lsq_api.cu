@@ -489,9 +489,102 @@ int run_classes(std::vector<lsqb200_plan::Class>& cls, cudaStream_t st) {
     return 0;
 }
 
+// ---- re-pointing a plan's per-step tensors: the new pointers travel as KERNEL ARGUMENTS of a one-CTA patch kernel (truly
+//      asynchronous, stream ordered, no pinned staging and no pageable cudaMemcpyAsync whose host side may wait for the stream).
+//      It is launched without the PDL attribute and never triggers its dependents early, so it starts after every earlier
+//      kernel that reads the table has finished and the next plan kernel starts after its writes are visible.
+constexpr int kPatchMax = 300;
+enum { PF_Y = 0, PF_G = 1, PF_GX = 2, PF_GSCALE = 3, PF_GSHIFT = 4 };
+struct PatchArgs {
+    Seg* table;
+    int n;
+    unsigned short seg[kPatchMax];
+    unsigned char field[kPatchMax];
+    const void* ptr[kPatchMax];
+};
+static_assert(sizeof(PatchArgs) <= 4000, "patch arguments must fit the 4 KB kernel parameter space");
+
+__global__ void lsq_plan_patch_kernel(const PatchArgs a) {
+    for (int i = threadIdx.x; i < a.n; i += blockDim.x) {
+        Seg& s = a.table[a.seg[i]];
+        void* p = const_cast<void*>(a.ptr[i]);
+        switch (a.field[i]) {
+            case PF_Y: s.y = p; break;
+            case PF_G: s.g = p; break;
+            case PF_GX: s.gx = p; break;
+            case PF_GSCALE: s.gscale = p; break;
+            default: s.gshift = p; break;
+        }
+    }
+}
+
+struct Patcher {
+    PatchArgs a;
+    cudaStream_t st;
+    int rc = 0;
+    Patcher(Seg* table, cudaStream_t s) : st(s) { a.table = table; a.n = 0; }
+    void flush() {
+        if (a.n == 0 || rc) return;
+        lsq_plan_patch_kernel<<<1, 128, 0, st>>>(a);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = cuda_fail(e, "plan patch launch");
+        a.n = 0;
+    }
+    void add(size_t seg, int field, const void* p) {
+        a.seg[a.n] = (unsigned short)seg; a.field[a.n] = (unsigned char)field; a.ptr[a.n] = p;
+        if (++a.n == kPatchMax) flush();
+    }
+};
+
+// same-or-better alignment than the pointer the geometry (unit width) was planned with
+bool keeps_alignment(const void* now, const void* before) { return common_alignment({now}) >= common_alignment({before}); }
+
 }  // namespace
 
 extern "C" {
+
+int lsqb200_plan_rebind(lsqb200_plan* plan, void* const* y, const void* const* grad, void* const* gx, void* const* gscale,
+                        void* const* gshift, void* stream) {
+    if (!plan) return fail(LSQB200_ERR_PLAN, "NULL plan");
+    const size_t n = plan->segs.size();
+    for (size_t i = 0; i < n; i++) {
+        lsqb200_segment& s = plan->segs[i];
+        if (s.outer * s.C * s.inner == 0) continue;
+        if ((y && (!y[i] || !keeps_alignment(y[i], s.y))) || (grad && (!grad[i] || !keeps_alignment(grad[i], s.grad))) ||
+            (gx && (!gx[i] || !s.gx || !keeps_alignment(gx[i], s.gx))) ||
+            (gscale && (!gscale[i] || !keeps_alignment(gscale[i], s.gscale))) || (gshift && (!gshift[i] || !keeps_alignment(gshift[i], s.gshift))))
+            return fail(LSQB200_ERR_PLAN, "rebind: NULL pointer, or less aligned than the pointer the plan was created with");
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        auto& classes = pass == 0 ? plan->fwd : plan->bwd;
+        if (pass == 0 ? !y : !(grad || gx || gscale || gshift)) continue;
+        for (auto& c : classes) {
+            if (c.host.empty() || !c.dev) continue;
+            if (c.host.size() > 65535) return fail(LSQB200_ERR_PLAN, "rebind: more than 65535 segments in one launch class");
+            Patcher pt(c.dev, (cudaStream_t)stream);
+            for (size_t j = 0; j < c.host.size(); j++) {
+                Seg& h = c.host[j];
+                const size_t i = (size_t)h.chan_stride;      // public segment index (see build_classes)
+                if (pass == 0) { h.y = y[i]; pt.add(j, PF_Y, y[i]); continue; }
+                if (grad) { h.g = grad[i]; pt.add(j, PF_G, grad[i]); }
+                if (gx) { h.gx = gx[i]; pt.add(j, PF_GX, gx[i]); }
+                if (gscale) { h.gscale = gscale[i]; pt.add(j, PF_GSCALE, gscale[i]); }
+                if (gshift) { h.gshift = gshift[i]; pt.add(j, PF_GSHIFT, gshift[i]); }
+            }
+            pt.flush();
+            if (pt.rc) return pt.rc;
+        }
+    }
+    for (size_t i = 0; i < n; i++) {
+        lsqb200_segment& s = plan->segs[i];
+        if (y) s.y = y[i];
+        if (grad) s.grad = grad[i];
+        if (gx) s.gx = gx[i];
+        if (gscale) s.gscale = gscale[i];
+        if (gshift) s.gshift = gshift[i];
+    }
+    return 0;
+}
 
 int lsqb200_abi_version(void) { return LSQB200_ABI_VERSION; }
 int64_t lsqb200_cuda_version(void) { return (int64_t)CUDA_VERSION; }

@@ -11,7 +11,7 @@ from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_in
 from pathlib import Path
 
 LIB_NAME = "libtorchlsq_b200.so"
-ABI_VERSION = 2          # LSQB200_ABI_VERSION of include/lsq_b200.h these prototypes were written against
+ABI_VERSION = 3          # LSQB200_ABI_VERSION of include/lsq_b200.h these prototypes were written against
 F32, F16, BF16, F64 = 0, 1, 2, 3
 SEM_LSQ, SEM_TORCH, SEM_TORCH_CPU = 0, 1, 2
 PRE_NONE, PRE_RELU, PRE_ADD_RELU, PRE_ADD = 0, 1, 2, 3   # fused prologue in front of the fake-quant (lsqb200_*_pre)
@@ -88,6 +88,8 @@ _PROTOTYPES = {
     "lsqb200_qparams": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p]),
     "lsqb200_flat_optimizer_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(OptimArgs), c_void_p]),
     "lsqb200_plan_create": (c_int, [POINTER(Segment), c_int32, POINTER(c_void_p)]),
+    "lsqb200_plan_rebind": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                    POINTER(c_void_p), c_void_p]),
     "lsqb200_plan_forward": (c_int, [c_void_p, c_void_p]),
     "lsqb200_plan_backward": (c_int, [c_void_p, c_void_p]),
     "lsqb200_plan_weight_init_stats": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -3,7 +3,7 @@
 behind `torch.ops.torchlsq.lsq` (see extension.py and include/lsq_b200.h)."""
 import torch
 from . import _cabi
-from .extension import _assert_has_ops, _lsq_front, _lsq_pre_front
+from .extension import _assert_has_ops
 
 
 Tensor = torch.Tensor
@@ -54,11 +54,6 @@ def lsq(x: Tensor, scale: Tensor, shift: Tensor,
     type_min = quant_min if type_min is None else type_min
     type_max = quant_max if type_max is None else type_max
 
-    if x.is_cuda:
-        # what torch.ops.torchlsq.lsq (CompositeImplicit, extension._lsq_front) does, called directly: one Python
-        # dispatcher hop less per call (tools/host_overhead.py)
-        return _lsq_front(x, scale, shift, quant_min, quant_max, type_min, type_max,
-                          axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel, eval_mode, init_mode)
     return torch.ops.torchlsq.lsq(x, scale, shift, quant_min, quant_max, type_min, type_max,
                                   axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel,
                                   eval_mode, init_mode)
@@ -75,8 +70,8 @@ def _pre(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max
         assert quant_min <= 0 <= quant_max, 'quantization range must be covered 0 in symmetric quantization'
     type_min = quant_min if type_min is None else type_min
     type_max = quant_max if type_max is None else type_max
-    return _lsq_pre_front(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max,
-                          axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel, eval_mode, init_mode)
+    return torch.ops.torchlsq.lsq_pre(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max,
+                                      axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel, eval_mode, init_mode)
 
 
 def lsq_relu(x: Tensor, scale: Tensor, shift: Tensor, quant_min: int = 0, quant_max: int = 255, type_min: int = None,

@@ -209,6 +209,7 @@ class LSQFakeQuantizer(ObserverBase):
             backward) instead of as a separate pass.  Results are bit-identical to the two-module sequence.
     """
     init_modes = ('learnable', 'observer')
+    _group_out = None      # (weight, fake-quantised weight) handed over by torchlsq.multi.group_weight_quantizers for this step
 
     @staticmethod
     def sign(x):
@@ -427,7 +428,28 @@ class LSQFakeQuantizer(ObserverBase):
         Same state machine and bit-identical results as `self(torch.relu(a + b))`."""
         return self._run(a, b, bool(relu))
 
+    # ---- hooks for torchlsq.multi.group_weight_quantizers (one launch for all weight quantizers of a model)
+    def _groupable(self, w) -> bool:
+        """Steady-state weight quantizer whose forward is exactly one `lsq` call on `w`."""
+        return (self._initialized and not self.debug_mode and self._m_fq == 1 and self._m_obs == 0 and self.otype == 0
+                and not self.fuse_relu and self.scale is not None and self.scale.dtype == torch.float32 and w.is_cuda
+                and w.dtype in (torch.float32, torch.float16, torch.bfloat16) and self.scale.device == w.device
+                and self.scale.numel() == (w.shape[self.ch_axis] if self.is_perchannel else 1))
+
+    def _type_range(self):
+        return TYPES_RANGE_MAPPING[self.dtype]['range']
+
+    def _prepare_params(self):
+        full_lsq = bool(self._m_learn)
+        self.scale.requires_grad = full_lsq
+        self.shift.requires_grad = full_lsq and self.is_affine
+
     def _run(self, x, x2, relu):
+        grouped = self._group_out
+        if grouped is not None:
+            self._group_out = None
+            if grouped[0] is x and x2 is None and not relu:
+                return grouped[1]
         # `pending`: the prologue (residual add and / or ReLU) still has to be applied to whatever we return or observe
         pending = relu or x2 is not None
 

@@ -38,7 +38,8 @@ def test_ctypes_prototypes_cover_the_header(native_lib):
 
 
 def test_info_calls_work_without_a_gpu(native_lib):
-    assert native_lib.lsqb200_abi_version() == 2
+    from torchlsq import _cabi
+    assert native_lib.lsqb200_abi_version() == _cabi.ABI_VERSION == 3
     v = native_lib.lsqb200_cuda_version()
     assert v // 1000 == 12            # CUDA 12.x toolchain (CUDA_VERSION, torchlsq.cpp:25-31 semantics)
     assert native_lib.lsqb200_workspace_bytes() >= 4096 * 4 + 16384 * 16
