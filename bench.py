@@ -258,7 +258,7 @@ def run_b200(args):
     assert flat.numel == 2 * (71 + 27_560)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     acts = []
-    for i, shp in enumerate(ACT_SHAPES):
+    for i, shp in enumerate([] if args.strong else ACT_SHAPES):
         n = B * math.prod(shp)
         x = torch.empty(n, dtype=torch.bfloat16, device=dev).normal_(0, 1, generator=gen)
         if i:
@@ -289,6 +289,8 @@ def run_b200(args):
 
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
+    if args.strong:
+        return run_strong_line(args, torch, dist, lib, flat, wplan, ws, sp, stream, dev, world, rank, local)
     qa = _cabi.qargs(0, 127, 0, 255, True, 1.0, False, False, False)
     fwd_calls, bwd_calls = [], []
     for a in acts:
@@ -426,16 +428,24 @@ def run_b200(args):
     if world == 1 and not args.no_fusion_mode:
         fusion_mode = run_fusion_mode(args, torch, lib, acts, flat, ws, sp, stream, wplan, qa, BF16, F32, dev, gen)
 
-    # ---- mu +- 3 sigma init throughput (one launch over all 54 weights)
-    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(3):
-        wplan.weight_init_stats(scales)
-    i0.record(stream)
-    for _ in range(10):
-        wplan.weight_init_stats(scales)
-    i1.record(stream)
-    torch.cuda.synchronize()
-    init_gbps = 4 * n_w / (i0.elapsed_time(i1) / 10 * 1e-3) / 1e9
+    # ---- every BASELINE config as its own measurement (L2 flushed between iterations where the working set is small)
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = peaks.get("hbm_gbs", 6650.0)
+    configs = None
+    if world == 1 and not args.no_configs:
+        try:
+            configs = run_configs(args, torch, lib, acts, wplan, ws, sp, stream, scales, dev, peak)
+        except Exception as exc:
+            configs = {"error": repr(exc)}
+    strong = None
+    if world == 1 and not args.no_strong:
+        try:
+            strong = run_strong(args, torch, dist, lib, flat, wplan, ws, sp, stream, dev, 1, peak)
+        except Exception as exc:
+            strong = {"error": repr(exc)}
 
     # ---- the same step through the PUBLIC API on device-resident tensors (the drop-in a user calls): functional op +
     #      autograd, and LSQFakeQuantizer modules
@@ -451,11 +461,6 @@ def run_b200(args):
     if not args.no_e2e:
         e2e = run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites)
 
-    peaks = {}
-    pk = ROOT / "MEASURED_PEAKS.json"
-    if pk.exists():
-        peaks = json.loads(pk.read_text())
-    peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     traffic = None
     prof = ROOT / "profiles" / "ncu_summary.json"
@@ -494,7 +499,7 @@ def run_b200(args):
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": bwd_bytes, "avg_ms_per_step": round(bwd_ms, 4)},
-            "api_mode": api_mode, "plan_mode": plan_mode, "prologue_fusion": fusion_mode, "weight_init_stats_GBps": round(init_gbps, 1), "dp_check": dp_check, "kernels_ran": ran_ok,
+            "api_mode": api_mode, "plan_mode": plan_mode, "prologue_fusion": fusion_mode, "configs": configs, "strong_batch2048": strong, "dp_check": dp_check, "kernels_ran": ran_ok,
             "allreduce": (None if world == 1 else ("inline on the compute stream" if args.inline_allreduce else
                                                    "side stream, overlapped with the next step's forward; joined in front of the next backward and before the final event")),
             "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
@@ -540,6 +545,271 @@ def run_dp_check(torch, dist, flat, world, fwd_calls, bwd_calls, fwd_t, bwd_t, w
                 "semantics": "sum over ranks of local-numel-scaled grads (lsq_cuda.cu:124,274)"}
     except Exception as exc:            # report, never kill the line
         return {"ok": False, "error": repr(exc)}
+
+
+def _timed_rotating(torch, fns, iters, stream, cover_us=60):
+    """Per-iteration CUDA-event timing over ROTATING buffer sets: iteration i runs fns[i % len(fns)], each on its own
+    tensors, the sets together well above the 126 MB L2 - "inputs larger than L2": nothing an iteration reads is left in L2
+    by an earlier one, and what an iteration leaves dirty in L2 is written back during the next (every byte crosses HBM
+    exactly once in steady state; no flush kernel, whose own dirty lines would be written back inside the timed region).
+    A spin kernel without memory traffic (torch.cuda._sleep) runs in front of every iteration so that the host has
+    enqueued the iteration's launches before the GPU reaches the first event: host latency is not counted.
+    Returns (median ms, best ms, back-to-back ms per iteration: all sets in a row between two events, no gaps)."""
+    spin = int(cover_us * 1.9e3)           # cycles at ~1.9 GHz
+    ts = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = len(fns)
+    for i in range(iters + 2 * n):
+        torch.cuda._sleep(spin)
+        e0.record(stream)
+        fns[i % n]()
+        e1.record(stream)
+        e1.synchronize()
+        if i >= 2 * n:
+            ts.append(e0.elapsed_time(e1))
+    reps = max(1, iters // n)
+    torch.cuda._sleep(spin)
+    e0.record(stream)
+    for _ in range(reps):
+        for f in fns:
+            f()
+    e1.record(stream)
+    e1.synchronize()
+    return statistics.median(ts), min(ts), e0.elapsed_time(e1) / (reps * n)
+
+
+def run_configs(args, torch, lib, acts, wplan, ws, sp, stream, scales, dev, peak):
+    """BASELINE.json configs[0..3] (configs[4] is the headline / `strong_batch2048`), plus the short-row per-channel layouts and
+    the observer step.  GB/s = algorithmic bytes / median time of one isolated iteration (see _timed_rotating): 5*sizeof(T) per
+    element for fwd+bwd, 1*sizeof(T) for statistics / observer; `GBps_stream` = the same work back to back."""
+    from torchlsq import _cabi
+    from torchlsq.multi import LSQPlan, Site
+    iters = max(8, min(args.steps, 20))
+    out = {"protocol": "per-iteration CUDA events over rotating buffer sets (total > 2x L2), spin-kernel cover for host latency, "
+                       "no flush kernel; median of %d" % iters}
+
+    def report(name, nbytes, timing, **extra):
+        med, best, stream_ms = timing
+        out[name] = dict(ms=round(med, 4), ms_best=round(best, 4), GBps=round(nbytes / med / 1e6, 1),
+                         frac=round(nbytes / med / 1e6 / peak, 4), GBps_stream=round(nbytes / stream_ms / 1e6, 1),
+                         frac_stream=round(nbytes / stream_ms / 1e6 / peak, 4), **extra)
+
+    # config 1: per-tensor quint8 fp32 32x64x56x56 (SURVEY 8d: seeds 1 / 2, scale .03, shift -1.7); 4 sets of 103 MB
+    R = 4
+    x0 = torch.randn(32, 64, 56, 56, generator=torch.Generator().manual_seed(1)).to(dev)
+    g0 = torch.randn(32, 64, 56, 56, generator=torch.Generator().manual_seed(2)).to(dev)
+    s, b = torch.tensor([0.03], device=dev), torch.tensor([-1.7], device=dev)
+    gs, gb = torch.empty(1, device=dev), torch.empty(1, device=dev)
+    q = _cabi.qargs(0, 127, 0, 255, True, 1.0, False, False, False)
+    n = x0.numel()
+    sets = [(x0.clone(), g0.clone(), torch.empty_like(x0), torch.empty_like(x0)) for _ in range(R)]
+
+    def c1(k):
+        x, g, y, gx = sets[k]
+        return lambda: (lib.lsqb200_fwd_tensor(x.data_ptr(), y.data_ptr(), s.data_ptr(), b.data_ptr(), n, 0, 0, q, sp),
+                        lib.lsqb200_bwd_tensor(g.data_ptr(), x.data_ptr(), gx.data_ptr(), s.data_ptr(), b.data_ptr(), gs.data_ptr(),
+                                               gb.data_ptr(), n, 0, 0, q, ws.data_ptr(), ws.numel(), sp))
+    report("config1_per_tensor_fp32_32x64x56x56", 5 * 4 * n, _timed_rotating(torch, [c1(k) for k in range(R)], iters, stream),
+           sets=R, launches=2)
+
+    def c1_ceiling(k):
+        x, g, y, gx = sets[k]
+        return lambda: (y.copy_(x), torch.add(x, g, out=gx))
+    report("config1_ceiling_aten_copy_plus_add", 5 * 4 * n, _timed_rotating(torch, [c1_ceiling(k) for k in range(R)], iters, stream),
+           sets=R, launches=2, note="the same bytes through ATen's own streaming kernels (copy R+W, add 2R+W): what two launches of this size reach")
+    del sets
+    # config 2: the 54 ResNet-50 weights, per-channel axis 0: the bench's plan + 3 more sets (408 MB each)
+    nw = sum(math.prod(sh) for sh in W_SHAPES)
+    plans, outs = [wplan], [scales]
+    gen = torch.Generator(device=dev).manual_seed(99)
+    for _ in range(R - 1):
+        st_ = []
+        for shp in W_SHAPES:
+            w = torch.empty(shp, device=dev).normal_(0, 0.05, generator=gen)
+            st_.append(Site(x=w, y=torch.empty_like(w), grad=torch.empty(shp, device=dev).normal_(generator=gen), gx=torch.empty_like(w),
+                            scale=torch.full((shp[0],), 0.002, device=dev), shift=torch.zeros(shp[0], device=dev),
+                            gscale=torch.empty(shp[0], device=dev), gshift=torch.empty(shp[0], device=dev), quant_min=-128, quant_max=127,
+                            type_min=-128, type_max=127, axis=0, is_affine=False, is_perchannel=True))
+        plans.append(LSQPlan(st_))
+        outs.append(torch.empty_like(scales))
+    report("config2_weight_init_mu3sigma_54_weights", 4 * nw,
+           _timed_rotating(torch, [(lambda p=p, o=o: p.weight_init_stats(o)) for p, o in zip(plans, outs)], iters, stream), sets=R, launches=1)
+    flats = [torch.empty(nw, device=dev).normal_() for _ in range(R)]
+    report("config2_weight_init_ceiling_aten_flat_sum", 4 * nw, _timed_rotating(torch, [(lambda f=f: f.sum()) for f in flats], iters, stream),
+           sets=R, note="one flat ATen reduction over the same number of bytes: no rows, no per-channel results")
+    del flats
+    report("config2_weights_fwd_bwd_54_weights", 5 * 4 * nw,
+           _timed_rotating(torch, [(lambda p=p: (p.forward(), p.backward())) for p in plans], iters, stream), sets=R,
+           launches=wplan.launches(False) + wplan.launches(True))
+    for p in plans[1:]:
+        p.close()
+    del plans, outs
+    # config 3: learned init (init_mode) on all 71 bf16 sites at the batch of this run (34 GB resident: one set)
+    qi = _cabi.qargs(0, 127, 0, 255, True, 1.0, False, False, True)
+    gsl, gbl = torch.empty(1, device=dev), torch.empty(1, device=dev)
+    f3 = [(a["x"].data_ptr(), a["y"].data_ptr(), a["s"].data_ptr(), a["b"].data_ptr(), a["n"], 2, 0, qi, sp) for a in acts]
+    b3 = [(a["g"].data_ptr(), a["x"].data_ptr(), a["gx"].data_ptr(), a["s"].data_ptr(), a["b"].data_ptr(), gsl.data_ptr(), gbl.data_ptr(),
+           a["n"], 2, 0, qi, ws.data_ptr(), ws.numel(), sp) for a in reversed(acts)]
+
+    def c3():
+        for c in f3:
+            lib.lsqb200_fwd_tensor(*c)
+        for c in b3:
+            lib.lsqb200_bwd_tensor(*c)
+    n3 = sum(a["n"] for a in acts)
+    report("config3_learned_init_bf16_71_sites", 5 * 2 * n3, _timed_rotating(torch, [c3], max(3, iters // 4), stream),
+           sets=1, resident_GB=round(4 * 2 * n3 / 1e9, 1), launches=2 * len(acts))
+    # config 4: per-channel axis 1, fp16 256x1024x28x28 (1.6 GB per set), fp32 parameters, grad scaling on; and the short-row layouts
+    N = 256
+    x4 = torch.empty(N * 1024 * 784, dtype=torch.float16, device=dev).normal_()
+    g4 = torch.empty_like(x4).normal_()
+    y4, gx4 = torch.empty_like(x4), torch.empty_like(x4)
+    for name, outer, cc, hw in (("config4_per_channel_fp16_256x1024x28x28", N, 1024, 784), ("per_channel_fp16_256x1024x14x14", N, 1024, 196),
+                                ("per_channel_fp16_256x2048x7x7", N, 2048, 49), ("per_channel_fp16_channels_last_50176x1024", N * 196, 1024, 1)):
+        sc, bc = 0.02 + 0.02 * torch.rand(cc, device=dev), -torch.rand(cc, device=dev)
+        gsc, gbc = torch.empty(cc, device=dev), torch.empty(cc, device=dev)
+        nn_ = outer * cc * hw
+        nset = max(1, (N * 1024 * 784) // nn_)          # rotate through disjoint slices of the 411 MB buffers
+
+        def c4(k):
+            o = k * nn_ * 2
+            return lambda: (lib.lsqb200_fwd_channel(x4.data_ptr() + o, y4.data_ptr() + o, sc.data_ptr(), bc.data_ptr(), outer, cc, hw, 1, 0, q, sp),
+                            lib.lsqb200_bwd_channel(g4.data_ptr() + o, x4.data_ptr() + o, gx4.data_ptr() + o, sc.data_ptr(), bc.data_ptr(),
+                                                    gsc.data_ptr(), gbc.data_ptr(), outer, cc, hw, 1, 0, q, ws.data_ptr(), ws.numel(), sp))
+        report(name, 5 * 2 * nn_, _timed_rotating(torch, [c4(k) for k in range(nset)], iters, stream), sets=nset, launches=2)
+    # observer-mode init step (SURVEY 8f-1) on a 411 MB bf16 activation: x4 / g4 / y4 / gx4 as four inputs
+    import warnings
+    from torchlsq.quantized.modules.observers import observer_step
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        obs = torch.quantization.MovingAverageMinMaxObserver(reduce_range=True).to(dev)
+    so, bo = torch.ones(1, device=dev), torch.zeros(1, device=dev)
+    xo = [t.view(torch.bfloat16) for t in (x4, g4, y4.normal_(), gx4.normal_())]
+    report("observer_step_bf16_411MB", 2 * xo[0].numel(), _timed_rotating(torch, [(lambda t=t: observer_step(obs, t, so, bo)) for t in xo], iters, stream),
+           sets=4, launches=1)
+    report("observer_step_ceiling_aten_amax_411MB", 2 * xo[0].numel(), _timed_rotating(torch, [(lambda t=t: t.amax()) for t in xo], iters, stream),
+           sets=4, note="ATen's own one-output reduction over the same bytes")
+    return out
+
+
+def run_strong(args, torch, dist, lib, flat, wplan, ws, sp, stream, dev, world, peak):
+    """BASELINE configs[4] as written: global batch 2048 split over `world` ranks, 71 bf16 activation sites + the 54
+    weights, forward of every site then backward of every site, flat-grad all-reduce when world > 1.  At world = 1 the largest
+    site is 2048x64x112x112 = 1.64 G elements (3.3 GB per buffer) and all sites together would need 275 GB, so the sites run one
+    at a time through four arenas (x, y, grad, grad_x) of 2x the largest site each, placed ring-fashion so that no site re-reads
+    what a recent one left in L2."""
+    from torchlsq import _cabi
+    B = 2048 // world
+    sizes = [B * math.prod(shp) for shp in ACT_SHAPES]
+    arena = 2 * max(sizes)
+    bufs = {}
+    for name in ("x", "g", "y", "gx"):
+        bufs[name] = torch.empty(arena, dtype=torch.bfloat16, device=dev)
+    chunk = 1 << 28
+    for o in range(0, arena, chunk):
+        bufs["x"][o:o + chunk].normal_().relu_()
+        bufs["g"][o:o + chunk].normal_()
+    esz = 2
+    base = {k: v.data_ptr() for k, v in bufs.items()}
+    q = _cabi.qargs(0, 127, 0, 255, True, 1.0, False, False, False)
+    s, b = torch.tensor([0.03], device=dev), torch.tensor([0.0], device=dev)
+    offs, off = [], 0
+    for n in sizes:
+        if off + n > arena:
+            off = 0
+        offs.append(off)
+        off += -(-n // 256) * 256
+    fcalls, bcalls = [], []
+    for i, (n, o) in enumerate(zip(sizes, offs)):
+        gs_, gb_ = flat.views(f"act{i}")
+        fcalls.append((base["x"] + o * esz, base["y"] + o * esz, s.data_ptr(), b.data_ptr(), n, _cabi.BF16, _cabi.F32, q, sp))
+        bcalls.append((base["g"] + o * esz, base["x"] + o * esz, base["gx"] + o * esz, s.data_ptr(), b.data_ptr(), gs_.data_ptr(),
+                       gb_.data_ptr(), n, _cabi.BF16, _cabi.F32, q, ws.data_ptr(), ws.numel(), sp))
+    bcalls.reverse()
+    pending = [None]
+
+    def step(ev0=None, ev1=None):
+        for c in fcalls:
+            lib.lsqb200_fwd_tensor(*c)
+        wplan.forward()
+        if pending[0] is not None:
+            pending[0].wait(); pending[0] = None
+        if ev0 is not None:
+            ev0.record(stream)
+        for c in bcalls:
+            lib.lsqb200_bwd_tensor(*c)
+        if ev1 is not None:
+            ev1.record(stream)
+        wplan.backward()
+        if world > 1:
+            pending[0] = flat.all_reduce(side_stream=not args.inline_allreduce)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(2, min(args.steps, 5 * world))
+    for _ in range(3):
+        step()
+    if pending[0] is not None:
+        pending[0].wait(); pending[0] = None
+    barrier()
+    bw = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(steps):
+        step(*bw[k])
+    if pending[0] is not None:
+        pending[0].wait(); pending[0] = None
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    n_act, n_w = sum(sizes), sum(math.prod(sh) for sh in W_SHAPES)
+    alg_rank = 5 * 2 * n_act + 5 * 4 * n_w
+    bwd_ms = statistics.mean(a.elapsed_time(b_) for a, b_ in bw)
+    dp_check = None
+    if world > 1:
+        dp_check = run_dp_check(torch, dist, flat, world, fcalls, bcalls, lib.lsqb200_fwd_tensor, lib.lsqb200_bwd_tensor, wplan)
+    return {"dp_check": dp_check, "value": round(alg_rank * world / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(ms, 4), "steps": steps,
+            "global_batch": 2048, "batch_per_gpu": B, "n_gpus": world, "per_gpu_GBps": round(alg_rank / (ms * 1e-3) / 1e9, 1),
+            "frac_of_measured_peak_per_gpu": round(alg_rank / (ms * 1e-3) / 1e9 / peak, 4),
+            "algorithmic_bytes_per_gpu_step": alg_rank, "elements_per_gpu_step": n_act + n_w,
+            "bwd_bf16_achieved_GBps": round(3 * 2 * n_act / (bwd_ms * 1e-3) / 1e9, 1), "bwd_ms_per_step": round(bwd_ms, 4),
+            "launches_per_step": 2 * len(sizes) + wplan.launches(False) + wplan.launches(True),
+            "arena": "x / y / grad / grad_x arenas of %.1f GB each (2x the largest site), sites placed ring-fashion" % (arena * esz / 1e9)}
+
+
+def run_strong_line(args, torch, dist, lib, flat, wplan, ws, sp, stream, dev, world, rank, local):
+    """`--strong`: the JSON line for BASELINE configs[4] as written (global batch 2048 over N ranks, strong scaling)."""
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak = peaks.get("hbm_gbs", 6650.0)
+    with ClockSampler(local) as clk:
+        r = run_strong(args, torch, dist, lib, flat, wplan, ws, sp, stream, dev, world, peak)
+    if rank == 0:
+        line = {"metric": "lsq_fwd_bwd_algorithmic_GBps", "value": r["value"], "unit": "GB/s", "n_gpus": world, "steps": r["steps"],
+                "warmup": 3, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "resnet50_qat_fakequant: BASELINE configs[4] as written - global batch 2048 split over the ranks "
+                                       "(71 bf16 per-tensor activation sites + 54 fp32 per-channel weights, fwd+bwd, flat-grad all-reduce when N>1)",
+                           "global_batch": 2048, "batch_per_gpu": r["batch_per_gpu"], "l2": r["arena"], "parallelism": f"dp{world}"},
+                "per_gpu_GBps": r["per_gpu_GBps"], "pct_of_hbm_peak_per_gpu": round(100 * r["frac_of_measured_peak_per_gpu"], 2),
+                "roofline": {"bound": "hbm", "kernel": "lsq_bwd_kernel<bf16> (per-tensor backward, 71 launches/step)",
+                             "achieved": r["bwd_bf16_achieved_GBps"], "peak": peak, "unit": "GB/s",
+                             "frac": round(r["bwd_bf16_achieved_GBps"] / peak, 4), "traffic": None},
+                "dp_check": r["dp_check"], "cpu_baseline": None, "e2e": None, "gpu_launches": r["launches_per_step"] * r["steps"],
+                "clocks": clk.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
 
 
 # per-image shapes of the sites that sit behind a ReLU / behind the residual add + ReLU of a block (torchvision resnet50)
@@ -882,6 +1152,11 @@ def main():
     ap.add_argument("--no-plan-mode", action="store_true", help="skip the extra multi-tensor-plan measurement")
     ap.add_argument("--plan-activations", action="store_true", help="run all activation sites through one multi-tensor plan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-BASELINE-config measurements (configs key)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the batch-2048 single-GPU point of BASELINE configs[4]")
+    ap.add_argument("--strong", action="store_true",
+                    help="BASELINE configs[4] as written: global batch 2048 split over the ranks (strong scaling), site at a time with "
+                         "buffer reuse; the JSON line then reports that job")
     ap.add_argument("--no-api-mode", action="store_true", help="skip the public-API (functional op / module) measurement")
     ap.add_argument("--inline-allreduce", action="store_true", help="N>1: all-reduce on the compute stream instead of the side stream")
     ap.add_argument("--no-fusion-mode", action="store_true", help="skip the workload-level prologue-fusion measurement")
