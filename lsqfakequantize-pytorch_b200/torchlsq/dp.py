@@ -98,6 +98,17 @@ class FlatLSQOptimizer:
     and one kernel launch, whatever the number of fake-quant sites.  The update is torch.optim.SGD's / Adam's
     single-tensor arithmetic in fp32 (csrc/kern_optim.cu).  Parameters that do not require grad (symmetric shifts, static
     quantizers) keep a zero gradient: with weight_decay = 0 they do not move.
+
+    Gradient aliasing: every `.grad` is a VIEW of the flat gradient buffer, which is what lets autograd accumulate straight
+    into it.  Use `opt.zero_grad()` (zeroes in place).  `model.zero_grad()` / another optimizer's `zero_grad()` default to
+    `set_to_none=True` and detach the views - autograd then allocates fresh gradients the flat buffer never sees; `step()`
+    detects that, copies such stray gradients into their slices and re-points `.grad`, so the update is still right (at
+    the price of one small copy per affected parameter and step).
+
+    Step counting: ONE counter drives Adam's bias correction and the SGD momentum-buffer initialisation for all parameters.
+    torch.optim skips parameters without a gradient, so its per-parameter counters start when a parameter first receives one
+    (after an observer init window, `scale.requires_grad` is False until then); build this optimizer after the init window -
+    or accept the usual warm-start difference of Adam's bias correction - if that matters.
     """
 
     def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter, Optional[torch.nn.Parameter]]], kind: str = "sgd",
@@ -135,6 +146,11 @@ class FlatLSQOptimizer:
                     pb.copy_(shift.detach().reshape(-1))
                     shift.data = pb.view_as(shift)
                     shift.grad = self.grads.gshift(name).view_as(shift)
+        self._grad_views = []          # (parameter, its slice of the flat gradient buffer, viewed in the parameter's shape)
+        for name, scale, shift in named_params:
+            self._grad_views.append((scale, self.grads.gscale(name).view_as(scale)))
+            if shift is not None:
+                self._grad_views.append((shift, self.grads.gshift(name).view_as(shift)))
         self.state1 = torch.zeros_like(self.params) if (kind == "adam" or momentum != 0) else None
         self.state2 = torch.zeros_like(self.params) if kind == "adam" else None
         self.steps = 0
@@ -153,8 +169,19 @@ class FlatLSQOptimizer:
         """Zero the flat gradient buffer in place (autograd keeps accumulating into the same slices)."""
         self.grads.zero_()
 
+    def _adopt_stray_grads(self):
+        """`.grad` tensors that no longer alias the flat buffer (set_to_none zero_grad, manual assignment): fold them in."""
+        for p, view in self._grad_views:
+            g = p.grad
+            if g is None:
+                p.grad = view                      # the slice holds zeros (zero_grad) or this step's kernel output
+            elif g.data_ptr() != view.data_ptr():
+                view.copy_(g.reshape(view.shape))  # autograd accumulated into a fresh tensor: that IS this step's gradient
+                p.grad = view
+
     def step(self):
         world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
+        self._adopt_stray_grads()
         self.grads.all_reduce(group=self.group)            # SUM; the 1/world of DDP-style averaging is folded into the update
         self.steps += 1
         a = self._cabi.OptimArgs(float(self.lr), float(self.weight_decay), 1.0 / world if self.average else 1.0, float(self.momentum),

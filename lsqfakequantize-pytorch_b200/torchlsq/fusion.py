@@ -110,13 +110,19 @@ def _is_relu_node(node, modules):
 
 def _is_add_node(node):
     import operator
+    inplace = False
     if node.op == "call_function" and node.target in (operator.add, operator.iadd, torch.add):
         ok = len(node.args) == 2 and not node.kwargs          # torch.add(a, b, alpha=...) is left alone
+        inplace = node.target is operator.iadd
     elif node.op == "call_method" and node.target in ("add", "add_"):
         ok = len(node.args) == 2 and not node.kwargs
+        inplace = node.target == "add_"
     else:
         return False
-    return ok and all(isinstance(a, torch.fx.Node) for a in node.args)
+    if not (ok and all(isinstance(a, torch.fx.Node) for a in node.args)):
+        return False
+    # `a += b` / `a.add_(b)` mutate a: if anything else reads a, dropping the add would hand that reader the pre-add value
+    return not inplace or len(node.args[0].users) == 1
 
 
 def fuse_prologues_fx(gm: "torch.fx.GraphModule", relu: bool = True, residual: bool = True) -> Dict[str, int]:

@@ -146,7 +146,9 @@ def observer_step(obs, x: Tensor, scale: Tensor, shift: Tensor) -> bool:
     if obs.min_val.numel() != nparam or (per_channel and obs.min_val.dim() != 1):
         obs.min_val.resize_(nparam).fill_(float("inf"))      # torch's "never observed" state
         obs.max_val.resize_(nparam).fill_(float("-inf"))
-    cache = obs.__dict__.get("_lsqb200_args")
+    key = (obs.quant_min, obs.quant_max, getattr(obs, "averaging_constant", 1.0), float(obs.eps), obs.qscheme, obs.dtype)
+    cached = obs.__dict__.get("_lsqb200_args")
+    cache = cached[1] if cached is not None and cached[0] == key else None
     if cache is None:
         sym = obs.qscheme in (torch.per_tensor_symmetric, torch.per_channel_symmetric)
         zp_sym = 0
@@ -154,7 +156,7 @@ def observer_step(obs, x: Tensor, scale: Tensor, shift: Tensor) -> bool:
             zp_sym = (obs.quant_min + obs.quant_max) // 2 if obs.has_customized_qrange else 128
         cache = _cabi.ObserverArgs(int(obs.quant_min), int(obs.quant_max), float(getattr(obs, "averaging_constant", 1.0)),
                                    float(obs.eps), int(moving), int(sym), int(zp_sym), 0)
-        obs.__dict__["_lsqb200_args"] = cache
+        obs.__dict__["_lsqb200_args"] = (key, cache)
     lib = _cabi.load()
     xd = x.detach()
     if per_channel:
@@ -304,6 +306,13 @@ class LSQFakeQuantizer(ObserverBase):
         # host mirrors of the four buffers: the state machine never reads device memory
         self._m_fq, self._m_obs, self._m_learn, self._m_batch = 1, 1, int(learn_params), 0
         self.enable_observer()
+
+    def sync_state(self) -> None:
+        """Re-read the four state buffers (one device->host read each).  The forward's state machine runs on host mirrors
+        of `fake_quant_enabled`, `observer_enabled`, `learning_enabled` and `current_batch`, kept current by the
+        enable_* / disable_* methods and by `load_state_dict`; call this after writing the buffers any other way (the
+        reference's style `mod.observer_enabled[0] = 0`, a DDP buffer broadcast, `load_state_dict(assign=True)`)."""
+        self._sync_mirrors()
 
     def _sync_mirrors(self):
         self._m_fq = int(self.fake_quant_enabled[0])

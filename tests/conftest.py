@@ -24,6 +24,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """GPU sessions: dump the achieved parity margins (tests/gpu_util.py::assert_grads_close) next to the other evidence."""
+    gu = sys.modules.get("gpu_util")
+    margins = getattr(gu, "MARGINS", None) if gu is not None else None
+    if not margins:
+        return
+    worst = {}
+    for rec in margins:
+        key = (rec["dtype"], rec["rel_bound"])
+        w = worst.setdefault(key, dict(dtype=rec["dtype"], rel_bound=rec["rel_bound"], calls=0, max_plain_rel_err=0.0,
+                                       max_plain_rel_err_where_cancellation_le_100=0.0, max_cancellation_ratio=0.0))
+        w["calls"] += 1
+        for k in ("max_plain_rel_err", "max_plain_rel_err_where_cancellation_le_100", "max_cancellation_ratio"):
+            w[k] = max(w[k], rec[k])
+    out = ROOT / "gpurun_out"
+    try:
+        out.mkdir(exist_ok=True)
+        (out / "parity_margins.json").write_text(json.dumps({"summary": list(worst.values()), "calls": len(margins)}, indent=1))
+    except OSError:
+        pass
+
+
 @pytest.fixture(scope="session")
 def golden_ops():
     data = np.load(GOLDEN / "ref_cpu_ops.npz")

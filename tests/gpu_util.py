@@ -134,6 +134,23 @@ def oracle_bwd(g, x, scale, shift, q, outer=1, C=1, inner=None, per_channel=Fals
                       ocfg(q, half_exact=half_exact, **kw), outer, C, inner, per_channel, dt=dt, with_abs=True)
 
 
+def stamped(report: dict) -> dict:
+    """Evidence files written by GPU tests carry when, on which device and by which build of the native library they were made,
+    so a skipped or stale run is visible (task 7c)."""
+    import hashlib
+    import time
+    out = dict(report)
+    path = _cabi.lib_path()
+    out["_provenance"] = dict(utc=time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), device=torch.cuda.get_device_name(0),
+                              libtorchlsq_b200_sha256_16=hashlib.sha256(path.read_bytes()).hexdigest()[:16],
+                              torch=torch.__version__)
+    return out
+
+
+MARGINS = []      # achieved parity margins of this session, written to gpurun_out/parity_margins.json (tests/conftest.py)
+CANCELLATION_LIMIT = 100.0
+
+
 def assert_grads_close(mine: torch.Tensor, ref: np.ndarray, mag: np.ndarray, rel, what=""):
     """|mine - ref| <= rel*|ref| + 1e-7*sum|terms| + output rounding.
 
@@ -141,10 +158,28 @@ def assert_grads_close(mine: torch.Tensor, ref: np.ndarray, mag: np.ndarray, rel
     fp32 (and it rounds term*gs per element, which the oracle reproduces and the kernels - which
     scale once, in fp64 - deliberately do not), so a sum of n terms carries ~2^-24*sum|t|/sqrt(n)
     of noise whatever the summation order; the kernels' own accumulation error (fp32 partials of
-    <= 32-64 terms, then fp64) is below that.  The reference's fp32 at::sum is ~10x looser."""
+    <= 32-64 terms, then fp64) is below that.  The reference's fp32 at::sum is ~10x looser.
+
+    On top of that bound (task 7a): fp32 results must meet the north_star's PLAIN 1e-6 relative error unless
+    the sum is cancellation-heavy (sum|terms| / |result| > 100), and the achieved plain relative error and that ratio are
+    recorded for every call so the margin is visible (gpurun_out/parity_margins.json)."""
     m = mine.double().cpu().numpy()
-    eps_out = {torch.float32: 2.0 ** -24, torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8}[mine.dtype]
+    ref = np.asarray(ref, dtype=np.float64).reshape(m.shape)
+    mag = np.asarray(mag, dtype=np.float64).reshape(m.shape)
+    eps_out = {torch.float32: 2.0 ** -24, torch.float16: 2.0 ** -11, torch.bfloat16: 2.0 ** -8, torch.float64: 2.0 ** -53}[mine.dtype]
     tol = rel * np.abs(ref) + 1e-7 * mag + eps_out * np.abs(ref) + 1e-30
-    bad = ~(np.abs(m - ref) <= tol)
+    err = np.abs(m - ref)
+    bad = ~(err <= tol)
     bad &= ~(np.isnan(m) & np.isnan(ref))
+    finite = np.isfinite(ref) & np.isfinite(m) & (np.abs(ref) > 0)
+    plain = np.where(finite, err / np.where(finite, np.abs(ref), 1.0), 0.0)
+    cancel = np.where(finite, mag / np.where(finite, np.abs(ref), 1.0), 0.0)
+    calm = finite & (cancel <= CANCELLATION_LIMIT)
+    MARGINS.append(dict(what=what, dtype=str(mine.dtype).replace("torch.", ""), n=int(m.size), rel_bound=rel,
+                        max_plain_rel_err=float(plain.max(initial=0.0)),
+                        max_plain_rel_err_where_cancellation_le_100=float(np.where(calm, plain, 0.0).max(initial=0.0)),
+                        max_cancellation_ratio=float(cancel.max(initial=0.0))))
     assert not bad.any(), (what, m[bad][:5], ref[bad][:5], tol[bad][:5])
+    if mine.dtype == torch.float32 and rel <= 1e-6:
+        over = calm & (plain > 1e-6 + eps_out)
+        assert not over.any(), (what, "plain relative error above 1e-6 without heavy cancellation", m[over][:5], ref[over][:5], cancel[over][:5])

@@ -300,4 +300,4 @@ def test_f64_bit_exact_against_reference_cuda_op(tmp_path):
             assert not bad.any(), (name, what, m[bad][:3], th[bad][:3])
         report[name] = dict(gs_mine=float(gs.flatten()[0]), gs_ref=float(r_["gs"].flatten()[0]))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / "ref_cuda_parity_f64.json").write_text(json.dumps(report, indent=1))
+    (ROOT / "gpurun_out" / "ref_cuda_parity_f64.json").write_text(json.dumps(U.stamped(report), indent=1))

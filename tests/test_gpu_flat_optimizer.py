@@ -130,3 +130,33 @@ def test_module_training_with_flat_optimizer_matches_torch_optim(kind, kw, tkw):
     assert torch.allclose(torch.tensor(l0), torch.tensor(l1), rtol=1e-4, atol=1e-5), (l0, l1)
     for a, b in zip(p0, p1):
         assert torch.allclose(a, b, rtol=2e-3, atol=1e-6), float((a - b).abs().max())
+
+
+def test_flat_optimizer_survives_set_to_none_zero_grad():
+    """`model.zero_grad()` (set_to_none=True, torch's default) detaches the .grad views from the flat buffer; autograd
+    then accumulates into fresh tensors.  step() must fold those back in - the parameters keep learning exactly as with
+    `opt.zero_grad()`."""
+    import torch.nn.functional as F
+    torch.backends.cudnn.deterministic = True
+    finals = []
+    for style in ("flat_zero_grad", "model_zero_grad"):
+        net, data = _net_and_data()
+        lsq_params = [p for n, p in net.named_parameters() if n.endswith(".scale") or n.endswith(".shift")]
+        flat = FlatLSQOptimizer.from_model(net, kind="sgd", lr=0.02, momentum=0.9)
+        before = [p.detach().clone() for p in lsq_params]
+        for x, t in data:
+            if style == "flat_zero_grad":
+                flat.zero_grad()
+                for p in net.parameters():
+                    if p not in lsq_params and p.grad is not None:
+                        p.grad = None
+            else:
+                net.zero_grad()                              # every .grad -> None, LSQ parameters included
+                flat.zero_grad()                             # the flat buffer itself still has to start from zero
+            F.cross_entropy(net(x), t).backward()
+            flat.step()
+            assert all(p.grad is not None and p.grad.data_ptr() >= flat.grads.flat.data_ptr() for p in lsq_params if p.requires_grad)
+        finals.append([p.detach().clone() for p in lsq_params])
+        assert any(not torch.equal(a, b) for a, b in zip(before, finals[-1]))       # they did move
+    for a, b in zip(*finals):
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-9), float((a - b).abs().max())

@@ -397,7 +397,7 @@ def test_bit_exact_against_reference_cuda_op(tmp_path):
             assert torch.allclose(gs, r_["gs"].float(), rtol=4e-3, atol=4e-3 * float(r_["gs"].float().abs().max())), (name, gs[:3], r_["gs"][:3])
         report[name] = dict(gs_mine=float(gs.flatten()[0]), gs_ref=float(r_["gs"].float().flatten()[0]))
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / "ref_cuda_parity.json").write_text(json.dumps(report, indent=1))
+    (ROOT / "gpurun_out" / "ref_cuda_parity.json").write_text(json.dumps(U.stamped(report), indent=1))
 
 
 # ------------------------------------------------------------------------------------------------

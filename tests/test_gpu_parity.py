@@ -505,3 +505,43 @@ def test_lean_weight_row_kernels_match_general(dt, shape, native_lib):
     general = _with_tuning(native_lib, "rowkernels=0", run)
     assert torch.equal(lean[0], general[0]) and torch.equal(lean[1], general[1])
     assert torch.allclose(lean[2], general[2], rtol=1e-6, atol=1e-12) and torch.allclose(lean[3], general[3], rtol=1e-6, atol=1e-12)
+
+
+def test_config4_full_size_gradients_vs_oracle():
+    """BASELINE config 4 at FULL size (256x1024x28x28 fp16, per-channel axis 1, grad scaling 1/sqrt(numel*qmax) with the whole
+    tensor's numel, lsq_cuda.cu:274): forward and grad_x bit-exact and all 1024 grad_scale / grad_shift values against the
+    oracle run over all 205 M elements (task 7b: no slab with its own gs)."""
+    N, C, H, W = 256, 1024, 28, 28
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(N, C, H * W, generator=gen, dtype=torch.float32).to(torch.float16).to(U.DEV)
+    g = torch.randn(N, C, H * W, generator=gen, dtype=torch.float32).to(torch.float16).to(U.DEV)
+    s = (0.02 + 0.02 * torch.rand(C, generator=gen)).to(U.DEV)
+    b = (-torch.rand(C, generator=gen)).to(U.DEV)
+    q = U.qa(use_gs=True)
+    y = U.fwd(x, s, b, q, N, C, H * W, True)
+    assert U.same_bits(y, U.oracle_fwd(x, s, b, q, N, C, H * W, True))
+    del y
+    gx, gs, gb = U.bwd(g, x, s, b, q, N, C, H * W, True)
+    ogx, ogs, ogb, ms, mb = U.oracle_bwd(g, x, s, b, q, N, C, H * W, True)
+    assert U.same_bits(gx, ogx)
+    U.assert_grads_close(gs, ogs, ms, 1e-6, "config4 full size gscale")
+    U.assert_grads_close(gb, ogb, mb, 1e-6, "config4 full size gshift")
+
+
+def test_config3_largest_site_full_size_vs_oracle():
+    """Largest ResNet-50 activation site of BASELINE config 3 (256x64x112x112 bf16, 205 M elements), learned-init mode and the
+    normal mode: every output element and both reductions against the oracle over the whole tensor."""
+    n = 256 * 64 * 112 * 112
+    x = torch.empty(n, dtype=torch.bfloat16, device=U.DEV).normal_(0, 1, generator=torch.Generator(U.DEV).manual_seed(0)).relu_()
+    g = torch.empty(n, dtype=torch.bfloat16, device=U.DEV).normal_(0, 1, generator=torch.Generator(U.DEV).manual_seed(1))
+    s, b = _params([0.03], [0.0])
+    for q, what in ((U.qa(init_mode=True), "learned init"), (U.qa(), "normal")):
+        y = U.fwd(x, s, b, q)
+        assert U.same_bits(y, U.oracle_fwd(x, s, b, q)), what
+        del y
+        gx, gs, gb = U.bwd(g, x, s, b, q)
+        ogx, ogs, ogb, ms, mb = U.oracle_bwd(g, x, s, b, q)
+        assert U.same_bits(gx, ogx), what
+        del gx, ogx
+        U.assert_grads_close(gs, ogs, ms, 1e-6, f"config3 largest site gscale ({what})")
+        U.assert_grads_close(gb, ogb, mb, 1e-6, f"config3 largest site gshift ({what})")

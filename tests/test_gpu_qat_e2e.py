@@ -114,5 +114,6 @@ def test_qat_training_matches_reference_package(tmp_path):
         za, zb = torch.tensor(a["qparams_zp"]), torch.tensor(b["qparams_zp"])
         assert (za - zb).abs().max() <= 1, (name, "zero_point")
         report[name] = dict(max_rel_scale_diff=float(((sa - sb).abs() / sb.abs().clamp_min(1e-12)).max()))
+    import gpu_util as U
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / "qat_e2e_vs_reference.json").write_text(json.dumps(report, indent=1))
+    (ROOT / "gpurun_out" / "qat_e2e_vs_reference.json").write_text(json.dumps(U.stamped(report), indent=1))
