@@ -1,6 +1,8 @@
 // kern_col.cu -- instantiations of the column-layout (short channel rows) kernels.
 // Variants (unit words, rows in flight, min CTAs/SM fwd / bwd): 0 = (4, 2, 4/3), 1 = (4, 4, 3/2), 2 = (2, 4, 6/4), 3 = (2, 8, 4/3),
-// 4 = (4, 2, 6/4), 5 = (4, 1, 6/4)
+// 4 = (4, 2, 6/4), 5 = (4, 1, 6/4).  Round 2 also measured software-pipelined forms (next row group's loads issued before the current
+// group is processed, two register buffers): within +-2 % of variant 1 on every short-row layout (profiles/r2_column_anatomy.md) - the
+// launches are bounded by per-CTA prologue / epilogue latency and SM imbalance, not by load latency inside the loop - so they were dropped.
 #include "lsq_column.cuh"
 #include "lsq_host.h"
 namespace lsqb200 {

@@ -52,25 +52,38 @@ template <typename T, int MODE, int CNW>
 struct SlotParams {
     static constexpr int VEC = ColVec<T, CNW>::VEC;
     float s[VEC], inv_s[VEC], zp[VEC];
-    __device__ __forceinline__ void load(const ColSeg& cs, long long unit_col) {
-        Seg fake;                       // make_chan only reads these fields
-        fake.per_channel = 1; fake.tmin = cs.tmin; fake.tmax = cs.tmax; fake.qmin = cs.qmin; fake.qmax = cs.qmax;
+    // The raw parameter loads are ISSUED first (issue), the caller then puts its first data loads in flight, and only then are
+    // the derived constants formed (finish): the thread's two dependent DRAM round trips (parameters, data) overlap instead of
+    // adding up, and make_chan (an IEEE division) runs once per DISTINCT channel of the unit, not once per slot (a 16-byte
+    // unit of a 7x7 / 14x14 map spans at most two channels).
+    float sraw[VEC], braw[VEC];
+    __device__ __forceinline__ void issue(const ColSeg& cs, long long unit_col) {
         // one 32-bit division for the first slot, then walk: L = C*inner < 2^31 is checked on the host
         const unsigned j0 = (unsigned)unit_col * VEC, inner = (unsigned)cs.inner;
         unsigned c = j0 / inner, r = j0 - c * inner;
-        float sraw[VEC], braw[VEC];
 #pragma unroll
-        for (int k = 0; k < VEC; k++) {          // issue every parameter load before the first use
+        for (int k = 0; k < VEC; k++) {
             sraw[k] = load_param(cs.scale, c, cs.pdt);
             braw[k] = load_param(cs.shift, c, cs.pdt);
             if (++r == inner) { r = 0; ++c; }
         }
+        r0 = j0 - (j0 / inner) * inner;
+    }
+    unsigned r0;     // position of slot 0 inside its channel
+    __device__ __forceinline__ void finish(const ColSeg& cs) {
+        Seg fake;                       // make_chan only reads these fields
+        fake.per_channel = 1; fake.tmin = cs.tmin; fake.tmax = cs.tmax; fake.qmin = cs.qmin; fake.qmax = cs.qmax;
+        const unsigned inner = (unsigned)cs.inner;
+        unsigned r = r0;
+        Chan cc;
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
-            const Chan cc = make_chan<MODE>(sraw[k], braw[k], fake);
+            if (k == 0 || r == 0) cc = make_chan<MODE>(sraw[k], braw[k], fake);     // slot k starts a new channel
             s[k] = cc.s; inv_s[k] = cc.inv_s; zp[k] = cc.zp;
+            if (++r == inner) r = 0;
         }
     }
+    __device__ __forceinline__ void load(const ColSeg& cs, long long unit_col) { issue(cs, unit_col); finish(cs); }
     __device__ __forceinline__ Chan chan(int k, const ColSeg& cs) const {
         Chan c;
         c.s = s[k]; c.inv_s = inv_s[k]; c.zp = zp[k]; c.qmin = cs.qmin; c.qmax = cs.qmax;
@@ -93,6 +106,31 @@ struct ColWalk {
         stride = ((long long)cs.units_per_row << sh) * ub;
     }
 };
+
+// The launch's last CTA turns the [C][2] fp64 accumulator into grad_scale / grad_shift and leaves it zeroed.  Eight channel
+// pairs per thread are loaded before the first store, so the tail of the launch costs one L2 round trip per 8 * THREADS
+// channels instead of one per THREADS (the stores may alias the loads as far as the compiler knows).
+template <int THREADS>
+__device__ __forceinline__ void col_finalise(const ColSeg& cs) {
+    constexpr int B = 8;
+    for (long long c0 = threadIdx.x; c0 < cs.C; c0 += (long long)B * THREADS) {
+        double2 v[B];
+#pragma unroll
+        for (int i = 0; i < B; i++) {
+            const long long c = c0 + (long long)i * THREADS;
+            v[i] = c < cs.C ? __ldcg(reinterpret_cast<const double2*>(cs.acc) + c) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int i = 0; i < B; i++) {
+            const long long c = c0 + (long long)i * THREADS;
+            if (c >= cs.C) continue;
+            store_param(cs.gscale, c, cs.pdt, v[i].x * cs.gs);
+            store_param(cs.gshift, c, cs.pdt, cs.sym ? 0.0 : v[i].y * cs.gs);
+            reinterpret_cast<double2*>(cs.acc)[c] = make_double2(0.0, 0.0);      // leave the workspace zeroed
+        }
+    }
+    if (threadIdx.x == 0) *cs.counter = 0u;
+}
 
 template <typename T, int MODE, bool INIT, int CNW, int kColUnroll, int MINB, int LD, int ST>
 __global__ void __launch_bounds__(kColThreads, MINB)
@@ -278,13 +316,7 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
     __syncthreads();
     if (!last_flag) return;
     __threadfence();
-    for (long long c = threadIdx.x; c < cs.C; c += kColThreads) {
-        const double a = __ldcg(cs.acc + 2 * c), b = __ldcg(cs.acc + 2 * c + 1);
-        store_param(cs.gscale, c, cs.pdt, a * cs.gs);
-        store_param(cs.gshift, c, cs.pdt, cs.sym ? 0.0 : b * cs.gs);
-        cs.acc[2 * c] = 0.0; cs.acc[2 * c + 1] = 0.0;      // leave the workspace zeroed
-    }
-    if (threadIdx.x == 0) *cs.counter = 0u;
+    col_finalise<kColThreads>(cs);
     }
 }
 
