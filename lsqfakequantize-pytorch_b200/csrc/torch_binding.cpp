@@ -477,6 +477,222 @@ Tensor lsq_pre_front(int64_t prologue, const Tensor& x_in, const c10::optional<T
     return LSQFunction::apply(x, x2, scale, shift, (int64_t)-1, prologue, LSQ_TAIL_ARGS);
 }
 
+// ---- grouped fake-quant: many sites (the conv / linear WEIGHTS of a model) behind ONE autograd node and one multi-tensor plan
+//      launch per direction (include/lsq_b200.h: lsqb200_plan_*).  New surface; the reference runs one op, one autograd node and
+//      1 + 3 + 2 kernels per site (ops/cuda/lsq_cuda.cu:56-58,128-141).  The plan (device-side descriptor table) is cached per
+//      group id and rebuilt only when an input's storage moves; the per-step tensors - outputs allocated afresh, the upstream
+//      gradients autograd hands over - are swapped in with lsqb200_plan_rebind (a tiny patch kernel, no sync).  Outputs and
+//      gradients are views of three flat buffers, so AccumulateGrad takes them over without a copy.
+struct GroupState {
+    lsqb200_plan* plan = nullptr;
+    std::vector<const void*> key;          // data pointers of xs, scales, shifts the plan was built for
+    Scalars s{};
+    int64_t axis = 0;
+    bool per_channel = true;
+    int64_t generation = 0, launches = 0;
+    std::mutex mu;
+    ~GroupState() { if (plan) lsqb200_plan_destroy(plan); }
+};
+std::mutex g_groups_mu;
+std::map<int64_t, std::shared_ptr<GroupState>>& groups() {
+    static auto& m = *new std::map<int64_t, std::shared_ptr<GroupState>>();
+    return m;
+}
+std::shared_ptr<GroupState> group_state(int64_t id) {
+    std::lock_guard<std::mutex> lock(g_groups_mu);
+    auto& m = groups();
+    auto it = m.find(id);
+    if (it == m.end()) it = m.emplace(id, std::make_shared<GroupState>()).first;
+    return it->second;
+}
+
+struct GroupLayout {      // element / parameter offsets of every site inside the flat buffers (32-byte aligned slices)
+    std::vector<int64_t> off, poff, nparam;
+    int64_t total = 0, ptotal = 0;
+};
+GroupLayout group_layout(at::TensorList xs, at::TensorList scales) {
+    GroupLayout L;
+    const size_t n = xs.size();
+    L.off.resize(n); L.poff.resize(n); L.nparam.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        L.off[i] = L.total;
+        L.total += (xs[i].numel() + 15) / 16 * 16;
+        L.poff[i] = L.ptotal;
+        L.nparam[i] = scales[i].numel();
+        L.ptotal += (scales[i].numel() + 7) / 8 * 8;
+    }
+    return L;
+}
+
+void group_check(at::TensorList xs, at::TensorList scales, at::TensorList shifts, int64_t axis, bool per_channel) {
+    const size_t n = xs.size();
+    TORCH_CHECK(n > 0 && scales.size() == n && shifts.size() == n, "lsq_group needs as many scale / shift tensors as inputs (and at least one)");
+    for (size_t i = 0; i < n; i++) {
+        check_common(xs[i], scales[i], shifts[i]);
+        TORCH_CHECK(xs[i].scalar_type() == xs[0].scalar_type() && xs[i].device() == xs[0].device() && xs[i].is_contiguous(),
+                    "lsq_group inputs must share dtype and device and be contiguous");
+        TORCH_CHECK(scales[i].scalar_type() == scales[0].scalar_type(), "lsq_group scale / shift tensors must share one dtype");
+        if (per_channel) check_channel(xs[i], scales[i], shifts[i], axis);
+        else TORCH_CHECK(scales[i].numel() == 1 && shifts[i].numel() == 1, "per-tensor sites take one scale / shift element");
+        TORCH_CHECK(xs[i].numel() > 0, "lsq_group inputs must not be empty");
+    }
+}
+
+// (re)build the cached plan when an input's storage moved; placeholders for the per-step tensors carry the alignment class
+void group_prepare(GroupState& g, at::TensorList xs, at::TensorList scales, at::TensorList shifts, const GroupLayout& L, int64_t axis,
+                   bool per_channel, const Scalars& s, const Tensor& flat_like) {
+    const size_t n = xs.size();
+    std::vector<const void*> key;
+    key.reserve(3 * n);
+    for (const auto& t : xs) key.push_back(t.data_ptr());
+    for (const auto& t : scales) key.push_back(t.data_ptr());
+    for (const auto& t : shifts) key.push_back(t.data_ptr());
+    const bool same_q = g.plan && g.axis == axis && g.per_channel == per_channel && g.s.quant_min == s.quant_min &&
+                        g.s.quant_max == s.quant_max && g.s.type_min == s.type_min && g.s.type_max == s.type_max &&
+                        g.s.use_grad_scaling == s.use_grad_scaling && g.s.grad_scaler == s.grad_scaler && g.s.sym == s.sym &&
+                        g.s.eval_mode == s.eval_mode && g.s.init_mode == s.init_mode;
+    if (g.plan && same_q && key == g.key) return;
+    if (g.plan) { lsqb200_plan_destroy(g.plan); g.plan = nullptr; }
+    // placeholders for the per-step tensors: never dereferenced (every run is preceded by a rebind of what it uses), they only
+    // tell the plan which alignment class - 32 bytes - the real buffers will have
+    Tensor pflat_like = at::empty({2 * L.ptotal}, scales[0].options());
+    std::vector<lsqb200_segment> segs(n);
+    const lsqb200_qargs q = s.q();
+    const int xd = dtype_code(xs[0].scalar_type()), pd = dtype_code(scales[0].scalar_type());
+    const int64_t es = xs[0].element_size(), ps = scales[0].element_size();
+    char* fb = static_cast<char*>(flat_like.data_ptr());
+    char* pb = static_cast<char*>(pflat_like.data_ptr());
+    for (size_t i = 0; i < n; i++) {
+        lsqb200_segment& sg = segs[i];
+        std::memset(&sg, 0, sizeof sg);
+        Box b = dense_box(xs[i], per_channel ? axis : -1);
+        sg.x = xs[i].data_ptr();
+        sg.y = fb + L.off[i] * es; sg.grad = sg.y; sg.gx = sg.y;
+        sg.scale = scales[i].data_ptr(); sg.shift = shifts[i].data_ptr();
+        sg.gscale = pb + L.poff[i] * ps; sg.gshift = pb + (L.ptotal + L.poff[i]) * ps;
+        sg.outer = b.outer; sg.C = b.C; sg.inner = b.inner;
+        sg.xdtype = xd; sg.pdtype = pd; sg.per_channel = per_channel ? 1 : 0; sg.prologue = LSQB200_PRE_NONE;
+        sg.q = q;
+    }
+    check_rc(lsqb200_plan_create(segs.data(), (int32_t)n, &g.plan), "lsqb200_plan_create");
+    g.key = std::move(key); g.s = s; g.axis = axis; g.per_channel = per_channel;
+    g.generation++;
+    g.launches = lsqb200_plan_launches(g.plan, 0) + lsqb200_plan_launches(g.plan, 1);
+}
+
+std::vector<Tensor> group_forward_cuda(at::TensorList xs, at::TensorList scales, at::TensorList shifts, int64_t axis, bool per_channel,
+                                       const Scalars& s, int64_t group) {
+    group_check(xs, scales, shifts, axis, per_channel);
+    const size_t n = xs.size();
+    const GroupLayout L = group_layout(xs, scales);
+    c10::cuda::OptionalCUDAGuard guard(xs[0].device());
+    void* stream = (void*)c10::cuda::getCurrentCUDAStream(xs[0].device().index()).stream();
+    Tensor flat = at::empty({L.total}, xs[0].options());
+    auto st = group_state(group);
+    std::lock_guard<std::mutex> lock(st->mu);
+    group_prepare(*st, xs, scales, shifts, L, axis, per_channel, s, flat);
+    std::vector<Tensor> ys(n);
+    std::vector<void*> yp(n);
+    for (size_t i = 0; i < n; i++) {
+        ys[i] = flat.as_strided(xs[i].sizes(), xs[i].strides(), L.off[i]);
+        yp[i] = ys[i].data_ptr();
+    }
+    check_rc(lsqb200_plan_rebind(st->plan, yp.data(), nullptr, nullptr, nullptr, nullptr, stream), "lsqb200_plan_rebind");
+    check_rc(lsqb200_plan_forward(st->plan, stream), "lsqb200_plan_forward");
+    return ys;
+}
+
+std::vector<Tensor> group_backward_cuda(const variable_list& grads, at::TensorList xs, at::TensorList scales, at::TensorList shifts,
+                                        int64_t axis, bool per_channel, const Scalars& s, int64_t group) {
+    const size_t n = xs.size();
+    const GroupLayout L = group_layout(xs, scales);
+    c10::cuda::OptionalCUDAGuard guard(xs[0].device());
+    void* stream = (void*)c10::cuda::getCurrentCUDAStream(xs[0].device().index()).stream();
+    Tensor flat = at::empty({L.total}, xs[0].options());
+    Tensor pflat = at::empty({2 * L.ptotal}, scales[0].options());
+    auto st = group_state(group);
+    std::lock_guard<std::mutex> lock(st->mu);
+    group_prepare(*st, xs, scales, shifts, L, axis, per_channel, s, flat);
+    std::vector<Tensor> keep(n), out(3 * n);
+    std::vector<const void*> gp(n);
+    std::vector<void*> gxp(n), gsp(n), gbp(n);
+    for (size_t i = 0; i < n; i++) {
+        Tensor g = grads[i];
+        if (!g.defined()) g = at::zeros_like(xs[i]);
+        else if (g.strides() != xs[i].strides() || g.scalar_type() != xs[i].scalar_type() || (reinterpret_cast<uintptr_t>(g.data_ptr()) & 31u))
+            g = at::empty_like(xs[i]).copy_(g.sizes() == xs[i].sizes() ? g : g.expand_as(xs[i]));
+        keep[i] = g;
+        gp[i] = g.data_ptr();
+        out[i] = flat.as_strided(xs[i].sizes(), xs[i].strides(), L.off[i]);
+        out[n + i] = pflat.as_strided({L.nparam[i]}, {1}, L.poff[i]);
+        out[2 * n + i] = pflat.as_strided({L.nparam[i]}, {1}, L.ptotal + L.poff[i]);
+        gxp[i] = out[i].data_ptr(); gsp[i] = out[n + i].data_ptr(); gbp[i] = out[2 * n + i].data_ptr();
+    }
+    check_rc(lsqb200_plan_rebind(st->plan, nullptr, gp.data(), gxp.data(), gsp.data(), gbp.data(), stream), "lsqb200_plan_rebind");
+    check_rc(lsqb200_plan_backward(st->plan, stream), "lsqb200_plan_backward");
+    // `keep` may die here: the kernels are queued on the stream the caching allocator frees the gradients on
+    return out;
+}
+
+class LSQGroupFunction : public torch::autograd::Function<LSQGroupFunction> {
+public:
+    static variable_list forward(AutogradContext* ctx, at::TensorList xs, at::TensorList scales, at::TensorList shifts, int64_t axis,
+                                 bool per_channel, int64_t group, int64_t quant_min, int64_t quant_max, int64_t type_min, int64_t type_max,
+                                 bool use_grad_scaling, double grad_scaler, bool sym, bool eval_mode, bool init_mode) {
+        const Scalars s = LSQ_SCALARS;
+        variable_list ys;
+        {
+            at::AutoDispatchBelowADInplaceOrView below;
+            ys = group_forward_cuda(xs, scales, shifts, axis, per_channel, s, group);
+        }
+        int64_t bits;
+        std::memcpy(&bits, &s.grad_scaler, sizeof bits);
+        const int64_t flags = (s.use_grad_scaling ? 1 : 0) | (s.sym ? 2 : 0) | (s.eval_mode ? 4 : 0) | (s.init_mode ? 8 : 0) | (per_channel ? 16 : 0);
+        ctx->saved_data["a"] = c10::IValue(std::vector<int64_t>{axis, group, flags, s.quant_min, s.quant_max, s.type_min, s.type_max, bits,
+                                                                   (int64_t)xs.size()});
+        variable_list saved;
+        saved.reserve(3 * xs.size());
+        for (const auto& t : xs) saved.push_back(t);
+        for (const auto& t : scales) saved.push_back(t);
+        for (const auto& t : shifts) saved.push_back(t);
+        ctx->save_for_backward(saved);
+        return ys;
+    }
+    static variable_list backward(AutogradContext* ctx, variable_list grad_output) {
+        TORCH_CHECK(!at::GradMode::is_enabled(), "double backwards on grouped lsq not supported");
+        const auto a = ctx->saved_data["a"].toIntVector();
+        Scalars s;
+        s.quant_min = a[3]; s.quant_max = a[4]; s.type_min = a[5]; s.type_max = a[6];
+        std::memcpy(&s.grad_scaler, &a[7], sizeof(double));
+        const int64_t flags = a[2];
+        s.use_grad_scaling = flags & 1; s.sym = flags & 2; s.eval_mode = flags & 4; s.init_mode = flags & 8;
+        const size_t n = (size_t)a[8];
+        const auto saved = ctx->get_saved_variables();
+        at::TensorList all(saved);
+        variable_list out = group_backward_cuda(grad_output, all.slice(0, n), all.slice(n, n), all.slice(2 * n, n), a[0], (flags & 16) != 0, s, a[1]);
+        out.resize(3 * n + 12);          // + the twelve non-tensor arguments
+        return out;
+    }
+};
+
+std::vector<Tensor> lsq_group(at::TensorList xs, at::TensorList scales, at::TensorList shifts, int64_t quant_min, int64_t quant_max,
+                              int64_t type_min, int64_t type_max, int64_t axis, bool use_grad_scaling, double grad_scaler, bool is_affine,
+                              bool is_perchannel, bool eval_mode, bool init_mode, int64_t group) {
+    TORCH_CHECK(!xs.empty() && xs[0].is_cuda(), "`input` tensor must be CUDA tensor (torchlsq-b200 has no CPU path)");
+    const bool sym = !is_affine;
+    return LSQGroupFunction::apply(xs, scales, shifts, axis, is_perchannel, group, LSQ_TAIL_ARGS);
+}
+void lsq_group_release(int64_t group) {
+    std::lock_guard<std::mutex> lock(g_groups_mu);
+    groups().erase(group);
+}
+// [plan generation (how often the device table was rebuilt), kernel launches of one forward + one backward]
+std::vector<int64_t> lsq_group_info(int64_t group) {
+    auto st = group_state(group);
+    std::lock_guard<std::mutex> lock(st->mu);
+    return {st->generation, st->launches};
+}
+
 int64_t cuda_version() { return lsqb200_cuda_version(); }
 int64_t binding_abi() { return lsqb200_abi_version(); }
 
@@ -494,6 +710,11 @@ TORCH_LIBRARY(torchlsq, m) {
     m.def("lsq_pre(int prologue, Tensor x, Tensor? x2, Tensor scale, Tensor shift, int quant_min, int quant_max, int type_min, "
           "int type_max, int axis, bool use_grad_scaling, float grad_scaler, bool is_affine, bool is_perchannel, bool eval_mode, "
           "bool init_mode) -> Tensor", &lsq_pre_front);
+    m.def("lsq_group(Tensor[] xs, Tensor[] scales, Tensor[] shifts, int quant_min, int quant_max, int type_min, int type_max, int axis, "
+          "bool use_grad_scaling, float grad_scaler, bool is_affine, bool is_perchannel, bool eval_mode, bool init_mode, int group) -> Tensor[]",
+          &lsq_group);
+    m.def("lsq_group_release(int group) -> ()", &lsq_group_release);
+    m.def("lsq_group_info(int group) -> int[]", &lsq_group_info);
     m.def("lsq_forward_per_tensor(Tensor x, Tensor scale, Tensor shift, " LSQ_TAIL_SCHEMA ") -> Tensor");
     m.def("lsq_backward_per_tensor(Tensor grad, Tensor x, Tensor scale, Tensor shift, " LSQ_TAIL_SCHEMA ") -> (Tensor, Tensor, Tensor)");
     m.def("lsq_forward_per_channel(Tensor x, Tensor scale, Tensor shift, int axis, " LSQ_TAIL_SCHEMA ") -> Tensor");

@@ -156,109 +156,64 @@ class LSQPlan:
 
 
 # ---- grouped fake-quant of many tensors behind ONE autograd node --------------------------------------------------------------
-class _GroupFunction(torch.autograd.Function):
-    """y_i = lsq(x_i, scale_i, shift_i) for every site of a group in one launch per direction (per kernel class).
-
-    Inputs: the group, then x_0..x_{n-1}, scale_0.., shift_0..; outputs y_0..y_{n-1}.  The backward runs once, when autograd has
-    the gradient of every output, and returns every grad_x / grad_scale / grad_shift: fresh views of three flat buffers, so
-    AccumulateGrad takes them over without a copy.  Bit-identical to n `torchlsq.functional.lsq` calls."""
-
-    @staticmethod
-    def forward(ctx, group, *tensors):
-        n = group.n
-        xs = tensors[:n]
-        plan = group._plan_for(tensors)
-        flat_y = torch.empty(group.total, dtype=group.dtype, device=group.device)
-        ys = [flat_y[o:o + m].view(x.shape) for (o, m), x in zip(group.spans, xs)]
-        plan.rebind(y=ys)
-        plan.forward()
-        ctx.group, ctx.plan = group, plan
-        ctx.save_for_backward(*tensors)        # version-checked like any saved tensor; the plan reads their storage
-        return tuple(ys)
-
-    @staticmethod
-    def backward(ctx, *grads):
-        if torch.is_grad_enabled():
-            raise RuntimeError("double backwards on grouped lsq not supported")
-        group, plan = ctx.group, ctx.plan
-        tensors = ctx.saved_tensors
-        n = group.n
-        xs = tensors[:n]
-        gs_in = []
-        for g, x in zip(grads, xs):
-            if g is None:
-                g = torch.zeros_like(x)
-            elif g.stride() != x.stride() or g.dtype != x.dtype or g.data_ptr() % 32:
-                g = torch.empty_like(x).copy_(g)
-            gs_in.append(g)
-        flat_gx = torch.empty(group.total, dtype=group.dtype, device=group.device)
-        flat_gp = torch.empty(2 * group.nparam, dtype=group.pdtype, device=group.device)
-        gxs = [flat_gx[o:o + m].view(x.shape) for (o, m), x in zip(group.spans, xs)]
-        gsc = [flat_gp[o:o + c] for o, c in group.pspans]
-        gsh = [flat_gp[group.nparam + o:group.nparam + o + c] for o, c in group.pspans]
-        plan.rebind(grad=gs_in, gx=gxs, gscale=gsc, gshift=gsh)
-        plan.backward()
-        return (None, *gxs, *gsc, *gsh)
+_group_ids = iter(range(1, 1 << 62))
 
 
 class LSQGroup:
     """Many fake-quant sites whose inputs are all known before any of them is needed - the conv / linear WEIGHTS of a
     model - quantised by one multi-tensor launch per direction instead of one launch (and one trip through the dispatcher
     and the autograd engine) per site.  `group()` returns the list of fake-quantised tensors, differentiable with respect
-    to every x, scale and shift.  All sites share dtype, device and the scalar arguments below; x_i must be contiguous.
+    to every x, scale and shift: ONE autograd node (`torch.ops.torchlsq.lsq_group`, csrc/torch_binding.cpp) whose backward
+    runs when autograd has the gradient of every output and hands back every grad_x / grad_scale / grad_shift as views of
+    three flat buffers (AccumulateGrad takes them over without a copy).  Bit-identical to n `torchlsq.functional.lsq` calls.
+    All sites share dtype, device and the scalar arguments below; x_i must be contiguous.
 
-    The plan (device-side table) is built at the first call and rebuilt only when an input tensor's storage moves."""
+    The plan (device-side descriptor table) is built at the first call and rebuilt only when an input's storage moves; the
+    per-step tensors are swapped in by `lsqb200_plan_rebind` (include/lsq_b200.h)."""
 
     def __init__(self, xs, scales, shifts, quant_min=-128, quant_max=127, type_min=None, type_max=None, axis=0,
                  use_grad_scaling=True, grad_scaler=1.0, is_affine=False, is_perchannel=True, eval_mode=False, init_mode=False):
+        from .extension import _assert_has_ops
+        _assert_has_ops()
         self.xs, self.scales, self.shifts = list(xs), list(scales), list(shifts)
         self.n = len(self.xs)
         if self.n == 0 or len(self.scales) != self.n or len(self.shifts) != self.n:
             raise ValueError("LSQGroup needs as many scale / shift tensors as inputs (and at least one)")
-        self.q = dict(quant_min=quant_min, quant_max=quant_max, type_min=type_min, type_max=type_max, axis=axis,
-                      use_grad_scaling=use_grad_scaling, grad_scaler=grad_scaler, is_affine=is_affine,
-                      is_perchannel=is_perchannel, eval_mode=eval_mode, init_mode=init_mode)
+        if not is_affine:
+            assert quant_min <= 0 <= quant_max, 'quantization range must be covered 0 in symmetric quantization'
+        self._args = (int(quant_min), int(quant_max), int(quant_min if type_min is None else type_min),
+                      int(quant_max if type_max is None else type_max), int(axis), bool(use_grad_scaling), float(grad_scaler),
+                      bool(is_affine), bool(is_perchannel), bool(eval_mode), bool(init_mode))
         x0 = self.xs[0]
-        self.dtype, self.device, self.pdtype = x0.dtype, x0.device, self.scales[0].dtype
-        self.spans, self.pspans = [], []
-        off = poff = 0
         for x, sc, sh in zip(self.xs, self.scales, self.shifts):
-            if x.dtype != self.dtype or x.device != self.device or not x.is_contiguous():
+            if x.dtype != x0.dtype or x.device != x0.device or not x.is_contiguous():
                 raise RuntimeError("LSQGroup inputs must share dtype and device and be contiguous")
-            if sc.dtype != self.pdtype or sh.dtype != self.pdtype:
+            if sc.dtype != self.scales[0].dtype or sh.dtype != self.scales[0].dtype:
                 raise RuntimeError("LSQGroup scale / shift tensors must share one dtype")
-            m = x.numel()
-            self.spans.append((off, m))
-            off += -(-m // 16) * 16                  # keep every view 32-byte aligned for 2- and 4-byte elements
-            c = sc.numel()
-            self.pspans.append((poff, c))
-            poff += -(-c // 8) * 8
-        self.total, self.nparam = off, poff
-        self._plan, self._key = None, None
-
-    def _plan_for(self, tensors):
-        key = tuple(t.data_ptr() for t in tensors)
-        if self._plan is None or key != self._key:
-            if self._plan is not None:
-                self._plan.close()
-            n = self.n
-            xs, scs, shs = tensors[:n], tensors[n:2 * n], tensors[2 * n:]
-            # placeholders with the alignment of the per-step buffers (rebind() swaps the real ones in before every run)
-            fy = torch.empty(self.total, dtype=self.dtype, device=self.device)
-            fp = torch.empty(2 * self.nparam, dtype=self.pdtype, device=self.device)
-            sites = []
-            for (o, m), (po, c), x, sc, sh in zip(self.spans, self.pspans, xs, scs, shs):
-                v = fy[o:o + m].view(x.shape)
-                sites.append(Site(x=x.detach(), scale=sc.detach(), shift=sh.detach(), y=v, grad=v, gx=v, gscale=fp[po:po + c],
-                                  gshift=fp[self.nparam + po:self.nparam + po + c], **self.q))
-            self._plan, self._key = LSQPlan(sites), key
-        return self._plan
+        self._id = next(_group_ids)
+        self._op = torch.ops.torchlsq.lsq_group
 
     def __call__(self):
-        return list(_GroupFunction.apply(self, *self.xs, *self.scales, *self.shifts))
+        return self._op(self.xs, self.scales, self.shifts, *self._args, self._id)
+
+    def info(self):
+        """(how often the device-side plan was (re)built, kernel launches of one forward + one backward)."""
+        gen, launches = torch.ops.torchlsq.lsq_group_info(self._id)
+        return gen, launches
 
     def launches(self):
-        return 0 if self._plan is None else self._plan.launches(False) + self._plan.launches(True)
+        return self.info()[1]
+
+    def close(self):
+        if getattr(self, "_id", None) is not None:
+            try:
+                torch.ops.torchlsq.lsq_group_release(self._id)
+            except Exception:
+                pass
+            self._id = None
+
+    def __del__(self):
+        self.close()
 
 
 def group_weight_quantizers(model: torch.nn.Module):
@@ -267,7 +222,10 @@ def group_weight_quantizers(model: torch.nn.Module):
     launch per direction.  A forward pre-hook on `model` quantises all weights up front; each quantizer then hands out
     its share when its module calls it.  Same results bit for bit; modules whose quantizer is not in steady state yet
     (parameters not created, fake-quant disabled, debug mode) or that transform the weight first (fused Conv-BN) simply keep
-    running on their own.  Returns the hook handle (`.remove()` undoes the grouping)."""
+    running on their own; the grouping is re-derived whenever a quantizer's state changes (enable_* / disable_* calls,
+    parameter creation, load_state_dict), not per step.  Attributes the state machine does not own (`debug_mode`,
+    `fuse_relu`, ranges) are read when the group is formed: call the helper again after changing them.
+    Returns the hook handle (`.remove()` undoes the grouping)."""
     from .quantized.modules.observers import LSQFakeQuantizer
     pairs = []
     for m in model.modules():
@@ -275,31 +233,41 @@ def group_weight_quantizers(model: torch.nn.Module):
         w = getattr(m, "weight", None)
         if isinstance(q, LSQFakeQuantizer) and isinstance(w, torch.nn.Parameter) and q.otype == 0:
             pairs.append((q, w))
-    state = {"group": None, "sig": None}
+    from .quantized.modules import observers as _obs
+    state = {"group": None, "ready": (), "epoch": -1}
 
-    def pre_hook(_module, _args):
+    def rebuild():
+        """Quantizers in steady state with identical settings form the group; the rest keep running on their own."""
+        state["group"], state["ready"] = None, ()
         ready = [(q, w) for q, w in pairs if q._groupable(w)]
-        for q, _ in pairs:
-            q._group_out = None
         if len(ready) < 2:
             return
-        q0 = ready[0][0]
-        sig = tuple((id(q), id(w), id(q.scale), id(q.shift), bool(q._m_learn)) for q, w in ready)
-        if sig != state["sig"]:
-            qs = [q for q, _ in ready]
-            if any((q.quant_min, q.quant_max, q.ch_axis, q.use_grad_scaling, q.grad_scaler, q.is_affine, q.is_perchannel, q.dtype,
-                    q._m_learn) != (q0.quant_min, q0.quant_max, q0.ch_axis, q0.use_grad_scaling, q0.grad_scaler, q0.is_affine,
-                                    q0.is_perchannel, q0.dtype, q0._m_learn) for q in qs) or \
-               any(w.dtype != ready[0][1].dtype or w.device != ready[0][1].device or not w.is_contiguous() for _, w in ready):
-                return                                  # heterogeneous quantizers: leave them alone
-            tmin, tmax = q0._type_range()
-            state["group"] = LSQGroup([w for _, w in ready], [q.scale for q in qs], [q.shift for q in qs], q0.quant_min, q0.quant_max,
-                                      tmin, tmax, q0.ch_axis, q0.use_grad_scaling, q0.grad_scaler, q0.is_affine, q0.is_perchannel,
-                                      eval_mode=not bool(q0._m_learn), init_mode=False)
-            state["sig"] = sig
+        q0, w0 = ready[0]
+        same = lambda q: (q.quant_min, q.quant_max, q.ch_axis, q.use_grad_scaling, q.grad_scaler, q.is_affine, q.is_perchannel, q.dtype,
+                          q._m_learn)
+        ready = [(q, w) for q, w in ready if same(q) == same(q0) and w.dtype == w0.dtype and w.device == w0.device and w.is_contiguous()]
+        if len(ready) < 2:
+            return
         for q, _ in ready:
             q._prepare_params()
-        for (q, w), y in zip(ready, state["group"]()):
-            q._group_out = (w, y)
+        tmin, tmax = q0._type_range()
+        state["group"] = LSQGroup([w for _, w in ready], [q.scale for q, _ in ready], [q.shift for q, _ in ready], q0.quant_min,
+                                  q0.quant_max, tmin, tmax, q0.ch_axis, q0.use_grad_scaling, q0.grad_scaler, q0.is_affine,
+                                  q0.is_perchannel, eval_mode=not bool(q0._m_learn), init_mode=False)
+        state["ready"] = tuple(ready)
+
+    def pre_hook(_module, _args):
+        # any flag change / parameter creation of any LSQFakeQuantizer bumps the epoch: only then is the grouping re-derived,
+        # so the steady-state cost of the hook is one op call plus one dict store per quantizer
+        if state["epoch"] != _obs.STATE_EPOCH[0]:
+            for q, _ in pairs:
+                q.__dict__["_group_out"] = None
+            rebuild()
+            state["epoch"] = _obs.STATE_EPOCH[0]
+        group = state["group"]
+        if group is None:
+            return
+        for (q, w), y in zip(state["ready"], group()):
+            q.__dict__["_group_out"] = (w, y)
 
     return model.register_forward_pre_hook(pre_hook)

@@ -81,6 +81,11 @@ def _with_args(cls_or_self, **kwargs):
     return _PartialWrapper(partial(cls_or_self, **kwargs))
 
 
+# bumped whenever any LSQFakeQuantizer's state-machine flags or parameters change; torchlsq.multi.group_weight_quantizers
+# re-derives its grouping only when it moved
+STATE_EPOCH = [0]
+
+
 class ObserverBase(torch.quantization.observer.ObserverBase):
     with_args = classmethod(_with_args)
 
@@ -146,7 +151,11 @@ def observer_step(obs, x: Tensor, scale: Tensor, shift: Tensor) -> bool:
     if obs.min_val.numel() != nparam or (per_channel and obs.min_val.dim() != 1):
         obs.min_val.resize_(nparam).fill_(float("inf"))      # torch's "never observed" state
         obs.max_val.resize_(nparam).fill_(float("-inf"))
-    key = (obs.quant_min, obs.quant_max, getattr(obs, "averaging_constant", 1.0), float(obs.eps), obs.qscheme, obs.dtype)
+    # the values baked into the cached argument struct; `eps` is a device buffer of the observer: its identity and version stand
+    # for its value (reading it would be a device->host sync per step)
+    eps = obs.eps
+    key = (obs.quant_min, obs.quant_max, getattr(obs, "averaging_constant", 1.0), id(eps), eps._version if isinstance(eps, torch.Tensor) else eps,
+           obs.qscheme, obs.dtype)
     cached = obs.__dict__.get("_lsqb200_args")
     cache = cached[1] if cached is not None and cached[0] == key else None
     if cache is None:
@@ -305,6 +314,7 @@ class LSQFakeQuantizer(ObserverBase):
         self.register_buffer('current_batch', torch.tensor([0], dtype=torch.int64))
         # host mirrors of the four buffers: the state machine never reads device memory
         self._m_fq, self._m_obs, self._m_learn, self._m_batch = 1, 1, int(learn_params), 0
+        STATE_EPOCH[0] += 1
         self.enable_observer()
 
     def sync_state(self) -> None:
@@ -319,6 +329,7 @@ class LSQFakeQuantizer(ObserverBase):
         self._m_obs = int(self.observer_enabled[0])
         self._m_learn = int(self.learning_enabled[0])
         self._m_batch = int(self.current_batch[0])
+        STATE_EPOCH[0] += 1
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
@@ -327,6 +338,7 @@ class LSQFakeQuantizer(ObserverBase):
     def _set_flag(self, name, mirror, value):
         getattr(self, name)[0] = value
         setattr(self, mirror, int(value))
+        STATE_EPOCH[0] += 1
 
     def check_is_init_mode(self):
         return bool(self._m_learn) and self.otype != 0 and self._m_batch <= self.n_batches
@@ -373,6 +385,7 @@ class LSQFakeQuantizer(ObserverBase):
         """Create `scale` / `shift` from the first tensor seen (observers.py:314-342).
         Parameters must be handed to the optimizer only after this first forward."""
         self._initialized = True
+        STATE_EPOCH[0] += 1
         per_ch = self.is_perchannel and x is not None
         size = (x.shape[self.ch_axis] if per_ch else 1,)
         device = x.device if x is not None else _init_device
@@ -456,7 +469,7 @@ class LSQFakeQuantizer(ObserverBase):
     def _run(self, x, x2, relu):
         grouped = self._group_out
         if grouped is not None:
-            self._group_out = None
+            self.__dict__["_group_out"] = None
             if grouped[0] is x and x2 is None and not relu:
                 return grouped[1]
         # `pending`: the prologue (residual add and / or ReLU) still has to be applied to whatever we return or observe

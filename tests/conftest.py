@@ -34,9 +34,11 @@ def pytest_sessionfinish(session, exitstatus):
     for rec in margins:
         key = (rec["dtype"], rec["rel_bound"])
         w = worst.setdefault(key, dict(dtype=rec["dtype"], rel_bound=rec["rel_bound"], calls=0, max_plain_rel_err=0.0,
+                                       max_plain_rel_err_where_cancellation_le_16=0.0,
                                        max_plain_rel_err_where_cancellation_le_100=0.0, max_cancellation_ratio=0.0))
         w["calls"] += 1
-        for k in ("max_plain_rel_err", "max_plain_rel_err_where_cancellation_le_100", "max_cancellation_ratio"):
+        for k in ("max_plain_rel_err", "max_plain_rel_err_where_cancellation_le_16", "max_plain_rel_err_where_cancellation_le_100",
+                  "max_cancellation_ratio"):
             w[k] = max(w[k], rec[k])
     out = ROOT / "gpurun_out"
     try:

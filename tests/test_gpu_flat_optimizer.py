@@ -142,14 +142,14 @@ def test_flat_optimizer_survives_set_to_none_zero_grad():
     for style in ("flat_zero_grad", "model_zero_grad"):
         net, data = _net_and_data()
         lsq_params = [p for n, p in net.named_parameters() if n.endswith(".scale") or n.endswith(".shift")]
+        others = [p for n, p in net.named_parameters() if not (n.endswith(".scale") or n.endswith(".shift"))]
         flat = FlatLSQOptimizer.from_model(net, kind="sgd", lr=0.02, momentum=0.9)
         before = [p.detach().clone() for p in lsq_params]
         for x, t in data:
             if style == "flat_zero_grad":
                 flat.zero_grad()
-                for p in net.parameters():
-                    if p not in lsq_params and p.grad is not None:
-                        p.grad = None
+                for p in others:
+                    p.grad = None
             else:
                 net.zero_grad()                              # every .grad -> None, LSQ parameters included
                 flat.zero_grad()                             # the flat buffer itself still has to start from zero
