@@ -266,7 +266,7 @@ LSQB200_API int lsqb200_query_launch(int64_t outer, int64_t C, int64_t inner, in
  * (also read once from $LSQB200_TUNE); not part of the reference surface.  Kernel-family switches, all with
  * bit-identical (flatkernels) or reduction-order-identical results: "flatkernels=0|1|2" (lean per-tensor forward [and
  * backward] for single launches; default 1), "rowkernels=0|1" (lean warp-per-row forward / backward for weight rows),
- * "rowstats=0..3" (lean warp-per-row statistics, variant), "column_path=0|1", "col_tma=0..3", "pdl=0|1". */
+ * "rowstats=0..7" (warp-per-row statistics: 1-3 descriptor form, 4-6 row-entry form, 7 bulk-copy ring; default 4), "column_path=0|1", "col_tma=0..3", "pdl=0|1". */
 LSQB200_API int lsqb200_set_tuning(const char* spec);
 
 #ifdef __cplusplus

@@ -25,12 +25,28 @@ KernelFn rowstats(int xdtype) {
     if (xdtype == DT_BF16) return lsq_rowstats_kernel<__nv_bfloat16, kThreads, U, kLd, MB>;
     return lsq_rowstats_kernel<__half, kThreads, U, kLd, MB>;
 }
+template <int U, int MB>
+KernelFn rowstats3(int xdtype) {
+    if (xdtype == DT_F32) return lsq_rowstats3_kernel<float, kThreads, U, kLd, MB>;
+    if (xdtype == DT_BF16) return lsq_rowstats3_kernel<__nv_bfloat16, kThreads, U, kLd, MB>;
+    return lsq_rowstats3_kernel<__half, kThreads, U, kLd, MB>;
+}
 }  // namespace
-// variant (Tuning::rowstats): 1 = four units in flight per lane, 4 CTAs/SM; 2 = two units, 6 CTAs/SM; 3 = one unit, 8 CTAs/SM
+// variant (Tuning::rowstats): 1 = four units in flight per lane, 4 CTAs/SM; 2 = two units, 6 CTAs/SM; 3 = one unit, 8 CTAs/SM;
+// row-entry table + pivot by shuffle (lsq_rowstats3_kernel, plans only): 4 = two units, 6 CTAs/SM; 5 = one unit, 8 CTAs/SM; 6 = four units, 4 CTAs/SM
 KernelFn get_rowstats_kernel(int xdtype, int variant) {
+    if (variant == 4) return rowstats3<2, 6>(xdtype);
+    if (variant == 5) return rowstats3<1, 8>(xdtype);
+    if (variant == 6) return rowstats3<4, 4>(xdtype);
     if (variant == 2) return rowstats<2, 6>(xdtype);
     if (variant == 3) return rowstats<1, 8>(xdtype);
     return rowstats<kRowStatsUnroll, kRowStatsMinBlocks>(xdtype);
+}
+// bulk-copy ring (Tuning::rowstats = 7): rows of whole 32-byte units, one resident CTA per SM, 128 KB ring
+KernelFn get_rowstats_ring_kernel(int xdtype) {
+    if (xdtype == DT_F32) return lsq_rowstats_ring_kernel<float>;
+    if (xdtype == DT_BF16) return lsq_rowstats_ring_kernel<__nv_bfloat16>;
+    return lsq_rowstats_ring_kernel<__half>;
 }
 KernelFn get_stats_kernel(int xdtype, int nw, int group) {
     if (xdtype == DT_F32) return pick<float>(nw, group);

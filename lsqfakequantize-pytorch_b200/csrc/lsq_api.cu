@@ -100,13 +100,23 @@ SegArgs seg_args(const void* x, void* y, const void* g, void* gx, const void* sc
 }
 
 int launch(KernelFn k, const Seg& seg, const Seg* table, const int* tile_seg, int nseg, long long tiles, long long grid,
-           cudaStream_t st) {
+           cudaStream_t st, int smem_bytes = 0) {
     if (grid <= 0) return 0;
     if (grid > 2147483647LL) return fail(LSQB200_ERR_ARG, "tensor too large for one launch");
+    if (smem_bytes > 48 * 1024) {     // opt in to large dynamic shared memory once per kernel
+        static std::mutex mu;
+        static std::map<const void*, int> done;
+        std::lock_guard<std::mutex> lk(mu);
+        if (done[(const void*)k] < smem_bytes) {
+            cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic shared memory)");
+            done[(const void*)k] = smem_bytes;
+        }
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap our prologue with the previous kernel's tail
@@ -373,6 +383,9 @@ struct lsqb200_plan {
         int* dev_tile_seg = nullptr;          // tile -> index into `dev`
         long long tiles = 0, grid = 0;
         int group = kThreads;
+        bool rowtable = false;                // dev_tile_seg holds one RowEntry per tile instead of a tile -> segment map (lsq_rowstats3_kernel)
+        int smem = 0;                         // dynamic shared memory of the launch (lsq_rowstats_ring_kernel)
+        bool resident = false;                // one CTA per SM walks the tiles (lsq_rowstats_ring_kernel)
     };
     std::vector<Class> fwd, bwd, stats;
     std::vector<lsqb200_segment> segs;
@@ -415,7 +428,12 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
         }
         else {
             if (s.xdtype == DT_F64) continue;   // no float64 statistics (the module cannot hold float64 weights): slot left untouched
-            if (row_kernels_eligible(g, s.xdtype) && tn.rowstats) { variant = 1; k = get_rowstats_kernel(s.xdtype, tn.rowstats); }
+            if (row_kernels_eligible(g, s.xdtype) && tn.rowstats) {
+                // rows that are whole 32-byte units take the bulk-copy ring (rowstats = 7); others the register-staged row kernels
+                const bool ring = tn.rowstats == 7 && (s.inner * (long long)elem_size(s.xdtype)) % 32 == 0;
+                variant = ring ? 3 : (tn.rowstats >= 4 ? 2 : 1);
+                k = ring ? get_rowstats_ring_kernel(s.xdtype) : get_rowstats_kernel(s.xdtype, tn.rowstats == 7 ? 4 : tn.rowstats);
+            }
             else k = get_stats_kernel(s.xdtype, g.nw, g.group);
         }
         if (!k) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
@@ -426,6 +444,8 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
             out.emplace_back();
             out.back().kernel = k;
             out.back().group = g.group;
+            out.back().rowtable = kind == K_STATS && variant >= 2;
+            if (kind == K_STATS && variant == 3) { out.back().smem = rowring::kSmemBytes; out.back().resident = true; }
         }
         lsqb200_plan::Class& c = out[it->second];
         double* partials = nullptr;
@@ -451,7 +471,32 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
     for (auto& c : out) {
         const long long gpc = (long long)(kThreads / c.group) * tiles_per_group(c.group);
         c.grid = (c.tiles + gpc - 1) / gpc;
+        if (c.resident && c.grid > (long long)tn.sm_count * rowring::kCtasPerSm) c.grid = (long long)tn.sm_count * rowring::kCtasPerSm;
     }
+    return 0;
+}
+
+// one 32-byte entry per row for lsq_rowstats3_kernel: row pointer, output slot relative to the class's first segment, length, denominator
+int upload_row_table(lsqb200_plan::Class& c, const lsqb200_plan* p) {
+    if (c.dev_tile_seg || c.tiles <= 0) return 0;
+    std::vector<RowEntry> rows((size_t)c.tiles);
+    const long long base = p->stats_offset[(size_t)c.host[0].chan_stride];
+    for (size_t i = 0; i < c.host.size(); i++) {
+        const Seg& h = c.host[i];
+        const lsqb200_segment& pub = p->segs[(size_t)h.chan_stride];
+        const long long b = h.tile_begin, e = (i + 1 < c.host.size()) ? c.host[i + 1].tile_begin : c.tiles;
+        const long long es = elem_size(pub.xdtype);
+        for (long long t = b; t < e; t++) {
+            RowEntry& r = rows[(size_t)t];
+            r.row = static_cast<const char*>(h.x) + (t - b) * h.inner * es;
+            r.out_rel = p->stats_offset[(size_t)h.chan_stride] + (t - b) - base;
+            r.inner = (int)h.inner; r.denom = h.stats_denom; r.pad[0] = r.pad[1] = 0;
+        }
+    }
+    cudaError_t e = cudaMalloc(&c.dev_tile_seg, rows.size() * sizeof(RowEntry));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan row table)");
+    e = cudaMemcpy(c.dev_tile_seg, rows.data(), rows.size() * sizeof(RowEntry), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(plan row table)");
     return 0;
 }
 
@@ -484,7 +529,7 @@ int upload_classes(std::vector<lsqb200_plan::Class>& cls) {
 int run_classes(std::vector<lsqb200_plan::Class>& cls, cudaStream_t st) {
     for (auto& c : cls) {
         if (c.host.empty()) continue;
-        if (int r = launch(c.kernel, c.host[0], c.dev, c.dev_tile_seg, (int)c.host.size(), c.tiles, c.grid, st)) return r;
+        if (int r = launch(c.kernel, c.host[0], c.dev, c.dev_tile_seg, (int)c.host.size(), c.tiles, c.grid, st, c.smem)) return r;
     }
     return 0;
 }
@@ -626,7 +671,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "column_max_row_bytes") g_tuning.column_max_row_bytes = v;
         else if (k == "rowkernels") g_tuning.rowkernels = v;
         else if (k == "flatkernels") g_tuning.flatkernels = v;
-        else if (k == "rowstats") g_tuning.rowstats = (v >= 0 && v <= 3) ? v : 2;
+        else if (k == "rowstats") g_tuning.rowstats = (v >= 0 && v <= 7) ? v : 4;
         else return fail(LSQB200_ERR_ARG, "tuning spec: unknown key");
         pos = end + 1;
     }
@@ -715,8 +760,11 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
                          C > 1, &q);
     a.stats_out = scale_out;
     const Seg seg = make_seg(a, g, partials, counters, 0);
-    KernelFn k = (row_kernels_eligible(g, xdtype) && tuning().rowstats) ? get_rowstats_kernel(xdtype, tuning().rowstats) : get_stats_kernel(xdtype, g.nw, g.group);
-    return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
+    const bool rows = row_kernels_eligible(g, xdtype) && tuning().rowstats;
+    // the row-entry kernels (variants >= 4) need a plan's table: single calls take the descriptor form
+    KernelFn k = rows ? get_rowstats_kernel(xdtype, tuning().rowstats >= 4 ? 2 : tuning().rowstats) : get_stats_kernel(xdtype, g.nw, g.group);
+    const long long grid = g.grid;
+    return launch(k, seg, nullptr, nullptr, 0, g.tiles, grid, (cudaStream_t)stream);
 }
 
 int lsqb200_observe(const void* x, int64_t outer, int64_t C, int64_t inner, int xdtype, int per_channel, float* min_val,
@@ -861,7 +909,7 @@ int lsqb200_plan_weight_init_stats(lsqb200_plan* plan, float* scale_out, void* s
         if (!c.dev) {
             cudaError_t e = cudaMalloc(&c.dev, c.host.size() * sizeof(Seg));
             if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(plan table)");
-            if (int r = upload_tile_map(c)) return r;
+            if (int r = c.rowtable ? upload_row_table(c, plan) : upload_tile_map(c)) return r;
         }
         cudaError_t e = cudaMemcpyAsync(c.dev, c.host.data(), c.host.size() * sizeof(Seg), cudaMemcpyHostToDevice,
                                         (cudaStream_t)stream);

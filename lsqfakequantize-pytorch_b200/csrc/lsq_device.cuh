@@ -928,13 +928,6 @@ lsq_rowstats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ 
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// Weight rows, forward and backward: the same lean warp-per-row shape as lsq_rowstats_kernel for the rows the plans of a
-// model consist of (every conv / linear weight with axis 0, 32-byte aligned rows of <= Tuning::warp_units units).  The
-// arithmetic is fq_forward / fq_backward<EXACT> exactly as in the warp-group instantiations of the general kernels (the
-// reference's fp32 terms bit for bit, summed in fp64); what is gone is the per-row descriptor staging, tile geometry, peel
-// logic and unit walker (~600 warp instructions per row, more than the work of a 4 KB row).
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ const Seg* find_segment(const Seg& single, const Seg* table, const int* tile_seg, int nseg, long long gtile) {
     if (table == nullptr) return &single;
     if (tile_seg != nullptr) return &table[tile_seg[gtile]];
@@ -942,6 +935,265 @@ __device__ __forceinline__ const Seg* find_segment(const Seg& single, const Seg*
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (table[mid].tile_begin <= gtile) lo = mid; else hi = mid - 1; }
     return &table[lo];
 }
+
+// ---------------------------------------------------------------------------------------------
+// lsq_rowstats_kernel with a SHORTER DEPENDENT CHAIN (round 2).  With 27 560 rows of ~4 KB (all conv / linear weights of
+// ResNet-50) the one-warp-per-row kernel is bound by the life of a warp, not by bandwidth: the same launch over bf16 weights
+// (half the bytes) takes 21.4 us against 26.6 us for fp32.  A warp's life is a chain of dependent round trips - tile map ->
+// descriptor -> pivot element -> row data -> reduction; here the plan holds one 32-byte ROW ENTRY per row (row pointer, output
+// slot, length, denominator: one broadcast load instead of two dependent ones) and the pivot comes out of the loaded data by
+// shuffle (lane 0's first unit starts with the row's first element), so the chain is entry -> data -> reduction.
+// Same arithmetic and summation order as lsq_rowstats_kernel: bit-identical scales.  (A persistent variant that also kept the
+// next row's entry and first units in flight measured slower, profiles/r2_rowstats.md.)
+// `tile_seg` carries the row-entry table; `single.stats_out` the base of the class's output slots.
+// ---------------------------------------------------------------------------------------------
+struct RowEntry {
+    const void* row;      // first element of the row
+    long long out_rel;    // output slot relative to the class's first segment
+    int inner;            // elements in the row
+    float denom;          // 2^bitness
+    int pad[2];
+};
+static_assert(sizeof(RowEntry) == 32, "one 256-bit load per row entry");
+
+template <typename T, int THREADS, int UNROLL, int LD, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+lsq_rowstats3_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                     long long total_tiles) {
+    constexpr int NW = 8, VEC = UnitOf<T, NW>::VEC, UB = 32, WARPS = THREADS / 32;
+    // the CTA's rows finish together: (s1, s2, pivot, length, denominator, slot) of every warp's row, then ONE warp runs the
+    // fp64 division / square-root chains of all of them side by side - they are ~45 % of the warp instructions of a launch
+    // when every warp runs them for its single row (ncu: 360 warp instructions per 4 KB row, 160 of them here)
+    __shared__ double fin_s1[WARPS], fin_s2[WARPS];
+    __shared__ float fin_pivot[WARPS], fin_denom[WARPS];
+    __shared__ int fin_inner[WARPS];
+    __shared__ long long fin_out[WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_trigger();
+    const long long gtile = (long long)blockIdx.x * WARPS + warp;
+    const bool live = gtile < total_tiles;
+    double s1 = 0.0, s2 = 0.0;
+    float pivot = 0.f, denom = 1.f;
+    int inner = 0;
+    long long out_rel = 0;
+    if (live) {
+        // plan tables are written at plan creation only: safe to read before the wait
+        const Raw<8> er = ld_unit<LD_DEFAULT, 8>(reinterpret_cast<const RowEntry*>(tile_seg) + gtile);
+        const T* rowp = reinterpret_cast<const T*>(((unsigned long long)er.w[1] << 32) | er.w[0]);
+        out_rel = (long long)(((unsigned long long)er.w[3] << 32) | er.w[2]);
+        inner = (int)er.w[4];
+        denom = __uint_as_float(er.w[5]);
+        const int mis = (int)(reinterpret_cast<uintptr_t>(rowp) & 31);
+        int head = mis ? (32 - mis) / (int)sizeof(T) : 0;
+        if (head > inner) head = inner;
+        const int units = (inner - head) / VEC;
+        const int tail = inner - head - units * VEC;
+        const char* p = reinterpret_cast<const char*>(rowp + head) + lane * UB;
+        pdl_wait();
+        Raw<NW> r[UNROLL];
+        if (units > 0) {
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++)          // lanes past the row end re-read a valid unit: loads stay unconditional
+                r[k] = ld_unit<LD, NW>(lane + 32 * k < units ? p + k * (32 * UB) : (lane < units ? p : reinterpret_cast<const char*>(rowp + head)));
+        }
+        if (head == 0 && units > 0) {                 // lane 0's first unit starts with the row's first element
+            float f0[VEC];
+            unpack_unit<T, NW>(r[0], f0);
+            pivot = __shfl_sync(0xffffffffu, f0[0], 0);
+        } else {
+            pivot = ElemTraits<T>::to_f(rowp[0]);
+        }
+        for (int i = lane; i < head + tail; i += 32) {
+            const int e = i < head ? i : head + units * VEC + (i - head);
+            const float d = __fsub_rn(ElemTraits<T>::to_f(rowp[e]), pivot);
+            s1 += (double)d; s2 += (double)__fmul_rn(d, d);
+        }
+        for (int u = lane; u < units; u += 32 * UNROLL) {
+            if (u != lane) {
+#pragma unroll
+                for (int k = 0; k < UNROLL; k++) r[k] = ld_unit<LD, NW>(p + (u + 32 * k < units ? k : 0) * (32 * UB));
+            }
+#pragma unroll
+            for (int k = 0; k < UNROLL; k++) {
+                if (u + 32 * k >= units) continue;
+                float f[VEC];
+                unpack_unit<T, NW>(r[k], f);
+                float u1 = 0.f, u2 = 0.f;
+#pragma unroll
+                for (int e = 0; e < VEC; e++) {
+                    const float d = __fsub_rn(f[e], pivot);
+                    u1 = __fadd_rn(u1, d); u2 = __fmaf_rn(d, d, u2);
+                }
+                s1 += (double)u1; s2 += (double)u2;
+            }
+            p += UNROLL * 32 * UB;
+        }
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+    }
+    if (lane == 0) {
+        fin_s1[warp] = s1; fin_s2[warp] = s2; fin_pivot[warp] = pivot; fin_denom[warp] = denom;
+        fin_inner[warp] = live ? inner : 0; fin_out[warp] = out_rel;
+    }
+    __syncthreads();
+    if (warp == 0 && lane < WARPS && fin_inner[lane] > 0)
+        single.stats_out[fin_out[lane]] = stats_scale(fin_s1[lane], fin_s2[lane], fin_pivot[lane], (double)fin_inner[lane], fin_denom[lane]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight-row statistics through a BULK-COPY RING (north_star: "TMA staging only where the per-channel layout - weight axis 0 -
+// makes tiles pay off").  The register-staged row kernels above keep 2 units per lane in flight for about a third of a warp's
+// short life (entry load - data - reduction): ~26 KB in flight per SM, 4.1 TB/s on the 27 560 rows of ResNet-50.  Here a warp
+// is persistent (rows r, r + W, ...; gridDim = SM count), prefetches the entries of its next 32 rows with ONE coalesced gather,
+// and its lane 0 keeps a private ring of S stages x 2 KB filled by cp.async.bulk (1-D bulk copies: rows are contiguous, no
+// tensor map needed) S chunks ahead of the lanes that consume them from shared memory: bytes in flight are set by the ring
+// (128 KB per SM), not by registers x occupancy x duty cycle, and nobody waits for a descriptor.
+// Only rows that are whole 32-byte units in 32-byte aligned tensors take this path (every conv / linear weight but a first
+// layer with K = 147); chunk = 64 units, lane l takes units l and l + 32 of each chunk, i.e. exactly the unit order of
+// lsq_rowstats_kernel: same fp32-per-unit / fp64-across-units arithmetic, bit-identical scales.
+// mbarrier / bulk-copy helpers are those of lsq_column.cuh (declared there; repeated locally to keep this header standalone).
+// ---------------------------------------------------------------------------------------------
+namespace rowring {
+constexpr int kStages = 4, kStageBytes = 2048, kWarps = 8, kCtasPerSm = 3;
+constexpr int kSmemBytes = kWarps * kStages * kStageBytes;      // 64 KB dynamic shared memory per CTA, three CTAs per SM
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ Raw<8> lds_unit32(uint32_t addr) {
+    Raw<8> r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]) : "r"(addr));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "r"(addr + 16));
+    return r;
+}
+}  // namespace rowring
+
+template <typename T>
+__global__ void __launch_bounds__(rowring::kWarps * 32, rowring::kCtasPerSm)
+lsq_rowstats_ring_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table, const int* __restrict__ tile_seg, int nseg,
+                         long long total_tiles) {
+    using namespace rowring;
+    constexpr int VEC = UnitOf<T, 8>::VEC;
+    extern __shared__ __align__(128) unsigned char ring_smem[];
+    __shared__ __align__(8) unsigned long long bars[kWarps * kStages];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_trigger();
+    const long long W = (long long)gridDim.x * kWarps;
+    const long long gw = (long long)blockIdx.x * kWarps + warp;
+    const uint32_t ring0 = s32(ring_smem) + (uint32_t)warp * (kStages * kStageBytes);
+    const uint32_t bar0 = s32(&bars[warp * kStages]);
+    if (lane == 0) {
+        for (int st = 0; st < kStages; st++) bar_init(bar0 + 8 * st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (gw >= total_tiles) return;
+    const long long my_rows = (total_tiles - gw + W - 1) / W;           // rows gw, gw + W, ...
+    const RowEntry* entries = reinterpret_cast<const RowEntry*>(tile_seg);
+    pdl_wait();
+    uint32_t issued = 0, consumed = 0;          // chunk counters of this warp (uniform across lanes)
+    for (long long base = 0; base < my_rows; base += 32) {
+        const int nb = my_rows - base < 32 ? (int)(my_rows - base) : 32;
+        // lane i: entry of the warp's (base + i)-th row - one gather, one latency for up to 32 rows
+        unsigned long long e_row = 0; long long e_out = 0; int e_bytes = 0; float e_den = 1.f; int e_inner = 0;
+        if (lane < nb) {
+            const Raw<8> er = ld_unit<LD_DEFAULT, 8>(entries + (gw + (base + lane) * W));
+            e_row = ((unsigned long long)er.w[1] << 32) | er.w[0];
+            e_out = (long long)(((unsigned long long)er.w[3] << 32) | er.w[2]);
+            e_inner = (int)er.w[4];
+            e_den = __uint_as_float(er.w[5]);
+            e_bytes = e_inner * (int)sizeof(T);
+        }
+        int prow = 0, poff = 0;                 // producer cursor: next chunk to issue (row index in this batch, byte offset)
+        int pbytes = __shfl_sync(0xffffffffu, e_bytes, 0);
+        unsigned long long pptr = __shfl_sync(0xffffffffu, e_row, 0);
+        auto issue_ahead = [&]() {              // uniform control flow; only lane 0 touches the barrier / copy engine
+            while (prow < nb && issued - consumed < (uint32_t)kStages) {
+                const int n = pbytes - poff < kStageBytes ? pbytes - poff : kStageBytes;
+                const uint32_t st = issued % kStages;
+                if (lane == 0) {
+                    bar_expect_tx(bar0 + 8 * st, (uint32_t)n);
+                    bulk_load(ring0 + st * kStageBytes, reinterpret_cast<const char*>(pptr) + poff, (uint32_t)n, bar0 + 8 * st);
+                }
+                issued++;
+                poff += n;
+                if (poff >= pbytes) {
+                    prow++; poff = 0;
+                    if (prow < nb) {
+                        pbytes = __shfl_sync(0xffffffffu, e_bytes, prow);
+                        pptr = __shfl_sync(0xffffffffu, e_row, prow);
+                    }
+                }
+            }
+        };
+        issue_ahead();
+        double k1 = 0.0, k2 = 0.0;              // lane i keeps the sums and the pivot of the batch's i-th row
+        float kp = 0.f;
+        for (int row = 0; row < nb; row++) {
+            const int rbytes = __shfl_sync(0xffffffffu, e_bytes, row);
+            float pivot = 0.f;
+            double s1 = 0.0, s2 = 0.0;
+            for (int off = 0; off < rbytes; off += kStageBytes) {
+                const int n = rbytes - off < kStageBytes ? rbytes - off : kStageBytes;
+                const uint32_t st = consumed % kStages;
+                bar_wait(bar0 + 8 * st, (consumed / kStages) & 1u);
+                const uint32_t sbase = ring0 + st * kStageBytes;
+                if (off == 0) {                 // the row's first element: the shift that keeps the sums small
+                    uint32_t w0;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w0) : "r"(sbase));
+                    float f0[ElemTraits<T>::PER_WORD];
+                    ElemTraits<T>::unpack_word(w0, f0);
+                    pivot = f0[0];
+                }
+                const int units = n >> 5;       // whole 32-byte units (rows on this path are multiples of 32 bytes)
+#pragma unroll
+                for (int k = 0; k < kStageBytes / 32 / 32; k++) {
+                    const int u = lane + 32 * k;
+                    if (u < units) {
+                        const Raw<8> r = lds_unit32(sbase + (uint32_t)u * 32u);
+                        float f[VEC];
+                        unpack_unit<T, 8>(r, f);
+                        float u1 = 0.f, u2 = 0.f;
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) {
+                            const float d = __fsub_rn(f[e], pivot);
+                            u1 = __fadd_rn(u1, d); u2 = __fmaf_rn(d, d, u2);
+                        }
+                        s1 += (double)u1; s2 += (double)u2;
+                    }
+                }
+                __syncwarp();                   // every lane is done with stage st: it may be refilled
+                consumed++;
+                issue_ahead();
+            }
+            s1 = warp_sum(s1); s2 = warp_sum(s2);       // butterfly: every lane holds the totals
+            if (lane == row) { k1 = s1; k2 = s2; kp = pivot; }
+        }
+        // the fp64 division / square root chains of up to 32 rows run side by side, one row per lane
+        if (lane < nb) single.stats_out[e_out] = stats_scale(k1, k2, kp, (double)e_inner, e_den);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight rows, forward and backward: the same lean warp-per-row shape as lsq_rowstats_kernel for the rows the plans of a
+// model consist of (every conv / linear weight with axis 0, 32-byte aligned rows of <= Tuning::warp_units units).  The
+// arithmetic is fq_forward / fq_backward<EXACT> exactly as in the warp-group instantiations of the general kernels (the
+// reference's fp32 terms bit for bit, summed in fp64); what is gone is the per-row descriptor staging, tile geometry, peel
+// logic and unit walker (~600 warp instructions per row, more than the work of a 4 KB row).
+// ---------------------------------------------------------------------------------------------
 
 template <typename T, int MODE, bool INIT, int THREADS, int UNROLL, int LD, int ST, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)

@@ -100,6 +100,7 @@ constexpr int kRowUnrollFwd = 2, kRowMinBlocksFwd = 6;   // units in flight per 
 constexpr int kRowUnrollBwd = 1, kRowMinBlocksBwd = 4;
 // weight rows (contiguous, 32-byte aligned, one warp each): see lsq_rowstats_kernel
 KernelFn get_rowstats_kernel(int xdtype, int variant);
+KernelFn get_rowstats_ring_kernel(int xdtype);
 constexpr int kRowStatsUnroll = 4;       // variant 1: 256-bit loads in flight per lane
 constexpr int kRowStatsMinBlocks = 4;    // variant 1: CTAs/SM (register cap 64: four 8-word units in flight need 32 registers alone)
 KernelFn get_observe_kernel(int xdtype, int nw, int group);
@@ -152,7 +153,7 @@ struct Tuning {
     // runs before its griddepcontrol.wait and overlaps the predecessor's reduction tail - so the backward stays general
     int flatkernels = 1;
     int rowkernels = 1;         // forward / backward over aligned weight rows: the lean warp-per-row kernels (0: the general warp-group kernels)
-    int rowstats = 2;           // mu +- 3 sigma over aligned weight rows: the lean warp-per-row kernel, variant 1 / 2 / 3 (kern_stats.cu); 0: the general kernel
+    int rowstats = 4;           // mu +- 3 sigma over aligned weight rows (kern_stats.cu): 1 / 2 / 3 descriptor form (x4 / x2 / x1 units in flight), 4 / 5 / 6 row-entry form (plans; default 4: x2, 6 CTAs/SM), 7 bulk-copy ring; 0: the general kernel
                                 // 54 ResNet-50 weights under ncu on B200: general kernel 34.5 us, variant 1 28.7, 2 25.2, 3 26.3
     // resident CTAs/SM the kernel family really gets (its __launch_bounds__): whole-wave rounding uses these.  The two-operand
     // ADD prologues run with 4 / 3 (tuning_for_mode below)

@@ -484,3 +484,35 @@ def test_module_observer_mode_native_equals_torch_path():
         if i >= 1:
             assert torch.equal(a.scale, b.scale) and torch.equal(a.shift, b.shift), i
     assert int(a.observer_enabled[0]) == 0 and int(b.observer_enabled[0]) == 0
+
+
+def test_weight_init_stats_kernel_variants_bit_identical():
+    """The statistics kernels of a plan - descriptor form (round 1), row-entry form (default) and the bulk-copy ring - share one
+    arithmetic and one summation order: the 27 560 ResNet-50 scales must agree bit for bit, rows that are not whole 32-byte
+    units (K = 147) included, and with the single-tensor call."""
+    import bench as B
+    from torchlsq import _cabi
+    from torchlsq.multi import LSQPlan, Site
+    from torchlsq.quantized.modules.observers import weight_init_scale
+    lib = _cabi.load()
+    gen = torch.Generator(device=U.DEV).manual_seed(5)
+    try:
+        for dtype in (torch.float32, torch.bfloat16):
+            ws = [torch.empty(s, device=U.DEV).normal_(0.01, 0.05, generator=gen).to(dtype) for s in B.W_SHAPES[:12] + B.W_SHAPES[-3:]]
+            sites = [Site(x=w, scale=torch.ones(w.shape[0], device=U.DEV), shift=torch.zeros(w.shape[0], device=U.DEV), quant_min=-128,
+                          quant_max=127, type_min=-128, type_max=127, axis=0, is_affine=False, is_perchannel=True) for w in ws]
+            outs = {}
+            for v in (2, 4, 5, 7):
+                lib.lsqb200_set_tuning(f"rowstats={v}".encode())
+                plan = LSQPlan(sites)                      # the kernel family is chosen at plan creation
+                a = plan.weight_init_stats()
+                b = plan.weight_init_stats(torch.empty_like(a))          # another output buffer: entries are relative, still right
+                assert torch.equal(a, b)
+                outs[v] = a.clone()
+                plan.close()
+            for v in (4, 5, 7):
+                assert torch.equal(outs[v].view(torch.int32), outs[2].view(torch.int32)), (dtype, v)
+            single = torch.cat([weight_init_scale(w, 0, True, -128, 127) for w in ws])
+            assert torch.equal(single.view(torch.int32), outs[2].view(torch.int32)), dtype
+    finally:
+        lib.lsqb200_set_tuning(b"")
