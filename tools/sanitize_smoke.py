@@ -108,5 +108,33 @@ for spec in (b"flatkernels=2", b"flatkernels=0,rowkernels=0,rowstats=0", b""):
             assert lib.lsqb200_weight_init_stats(x.data_ptr(), so.data_ptr(), 1, C, n // C, _cabi.F32 if dt == torch.float32 else _cabi.BF16,
                                                  -128, 127, U.workspace().data_ptr(), U.workspace().numel(), U.stream()) == 0
             torch.cuda.synchronize()
+# round 2: plan statistics in the row-entry form (default) and through the bulk-copy ring (mbarrier + cp.async.bulk), rows that are
+# whole 32-byte units and rows that are not; plan_rebind (patch kernel) and the grouped op behind autograd
+for spec in (b"rowstats=2", b"rowstats=4", b"rowstats=7"):
+    assert lib.lsqb200_set_tuning(spec) == 0
+    outs = []
+    for dt in (torch.float32, torch.bfloat16):
+        ws_ = [(torch.randn(*shp, generator=gen) * 0.05).to(dt).to(U.DEV) for shp in ((16, 3, 7, 7), (40, 16, 1, 1), (24, 8, 3, 3), (9, 1024), (70, 64))]
+        st_ = [Site(x=w, scale=torch.ones(w.shape[0], device=U.DEV), shift=torch.zeros(w.shape[0], device=U.DEV), quant_min=-128, quant_max=127,
+                    type_min=-128, type_max=127, axis=0, is_affine=False, is_perchannel=True) for w in ws_]
+        p_ = LSQPlan(st_)
+        o_ = p_.weight_init_stats(); o2_ = p_.weight_init_stats(torch.empty_like(o_))
+        torch.cuda.synchronize()
+        assert torch.equal(o_, o2_) and torch.isfinite(o_).all()
+        p_.close()
 lib.lsqb200_set_tuning(b"")
+from torchlsq.multi import LSQGroup
+gw = [(torch.randn(*shp, generator=gen) * 0.05).to(U.DEV).requires_grad_(True) for shp in ((16, 3, 7, 7), (32, 16, 1, 1), (8, 8, 3, 3), (10, 64))]
+gsc = [torch.full((w.shape[0],), 0.002, device=U.DEV, requires_grad=True) for w in gw]
+gsh = [torch.zeros(w.shape[0], device=U.DEV, requires_grad=True) for w in gw]
+grp = LSQGroup(gw, gsc, gsh, -128, 127, -128, 127, axis=0, is_affine=False, is_perchannel=True)
+from torchlsq.functional import lsq as _lsq
+for _ in range(2):
+    ys = grp()
+    torch.autograd.backward(ys, [torch.randn(*w.shape, generator=gen).to(U.DEV) for w in gw])
+    for w, a, b_, y in zip(gw, gsc, gsh, ys):
+        assert torch.equal(y, _lsq(w.detach(), a.detach(), b_.detach(), -128, 127, -128, 127, axis=0, is_affine=False, is_perchannel=True))
+        w.grad = a.grad = b_.grad = None
+torch.cuda.synchronize()
+grp.close()
 print("sanitize_smoke ok")
