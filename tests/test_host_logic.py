@@ -345,3 +345,45 @@ def test_fuse_prologues_fx_rewrites_single_user_chains_only():
     assert not any(m.fuse_relu for m in modules.values() if isinstance(m, LSQFakeQuantizer))   # graph mode keeps the flag per call
     assert "forward" in gm.conv1.__dict__                                       # ConvBnReLU2d lost its F.relu
     assert fuse_prologues_fx(gm) == {"relu": 0, "residual": 0}
+
+
+def test_round2_binding_entries_on_cpu():
+    """torchlsq/_C.so (csrc/torch_binding.cpp) also registers the fused-prologue op and the grouped op; without a GPU they must be
+    present with their schemas, refuse CPU tensors loudly (no CPU path) and keep their bookkeeping calls harmless."""
+    import torchlsq  # noqa: F401
+    from torchlsq.multi import LSQGroup
+    assert "Tensor[] xs, Tensor[] scales, Tensor[] shifts" in str(torch.ops.torchlsq.lsq_group.default._schema)
+    assert str(torch.ops.torchlsq.lsq_pre.default._schema).startswith("torchlsq::lsq_pre(int prologue, Tensor x, Tensor? x2, Tensor scale, Tensor shift")
+    assert torch.ops.torchlsq._b200_abi_version() == 3
+    w = [torch.randn(4, 3), torch.randn(5, 3)]
+    sc = [torch.ones(4), torch.ones(5)]
+    sh = [torch.zeros(4), torch.zeros(5)]
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        torch.ops.torchlsq.lsq_group(w, sc, sh, -128, 127, -128, 127, 0, True, 1.0, False, True, False, False, 12345)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        torch.ops.torchlsq.lsq_pre(1, w[0], None, sc[0], sh[0], 0, 127, 0, 255, 1, True, 1.0, True, False, False, False)
+    assert list(torch.ops.torchlsq.lsq_group_info(12345)) == [0, 0]
+    torch.ops.torchlsq.lsq_group_release(12345)
+    with pytest.raises(ValueError):
+        LSQGroup([], [], [])
+    with pytest.raises(RuntimeError, match="dtype"):
+        LSQGroup([w[0], w[1].half()], sc, sh)
+    with pytest.raises(AssertionError, match="symmetric"):
+        LSQGroup(w, sc, sh, quant_min=1, quant_max=5, is_affine=False)
+    g = LSQGroup(w, sc, sh)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        g()
+    g.close()
+
+
+def test_state_epoch_moves_with_the_state_machine():
+    """group_weight_quantizers re-derives its grouping only when this counter moved: every flag change and parameter creation must bump it."""
+    from torchlsq import LSQFakeQuantizer
+    from torchlsq.quantized.modules import observers as obs
+    q = LSQFakeQuantizer(None, 'weight', dtype=torch.qint8, qscheme=torch.per_channel_symmetric, init_mode='learnable')
+    seen = [obs.STATE_EPOCH[0]]
+    for action in (q.disable_fake_quant, q.enable_fake_quant, q.enable_static_estimate, q.enable_param_learning, q.sync_state,
+                   lambda: q.load_state_dict(q.state_dict()), q.reset):
+        action()
+        assert obs.STATE_EPOCH[0] > seen[-1], action
+        seen.append(obs.STATE_EPOCH[0])
