@@ -7,6 +7,6 @@ Public surface kept from the reference (/root/reference/torchlsq/__init__.py:1-1
 """
 from .extension import _HAS_OPS
 
-__version__ = "2.1+b200.r1"
+__version__ = "2.1+b200.r2"
 
 from .quantized import *  # noqa: F401,F403,E402
