@@ -260,7 +260,8 @@ int forward_common(const void* x, const void* x2, void* y, const void* scale, co
     const Geometry g = plan_geometry(outer, C, inner, xdt, K_FWD, common_alignment({x, x2, y}), tuning_for_mode(tuning(), mode));
     SegArgs a = seg_args(x, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, xdt, pdt, per_channel, q);
     a.x2 = x2;
-    const Seg seg = make_seg(a, g, nullptr, nullptr, 0);
+    Seg seg = make_seg(a, g, nullptr, nullptr, 0);
+    seg.flags = tuning().l2_prefetch;
     if (mode == M_FP32 && tuning().flatkernels && flat_eligible(g, xdt))
         return launch_flat(get_flatfwd_kernel(xdt, q->init_mode != 0), seg, g.grid, (cudaStream_t)stream);
     KernelFn k = (mode == M_FP32 && tuning().rowkernels && row_kernels_eligible(g, xdt)) ? get_rowfwd_kernel(xdt, q->init_mode != 0)
@@ -333,7 +334,8 @@ int backward_common(const void* grad, const void* x, const void* x2, void* gx, c
     }
     SegArgs a = seg_args(x, nullptr, grad, gx, scale, shift, gscale, gshift, outer, C, inner, xdt, pdt, per_channel, q);
     a.x2 = x2;
-    const Seg seg = make_seg(a, g, partials, counters, 0);
+    Seg seg = make_seg(a, g, partials, counters, 0);
+    seg.flags = tuning().l2_prefetch;
     if (mode == M_FP32 && tuning().flatkernels >= 2 && flat_eligible(g, xdt))
         return launch_flat(get_flatbwd_kernel(xdt, bmode_of(q)), seg, g.grid, st);
     KernelFn k = (mode == M_FP32 && tuning().rowkernels && row_kernels_eligible(g, xdt)) ? get_rowbwd_kernel(xdt, bmode_of(q))
@@ -462,6 +464,7 @@ int build_classes(lsqb200_plan* p, int kind, std::vector<lsqb200_plan::Class>& o
                              s.xdtype, s.pdtype, s.per_channel, &s.q);
         a.x2 = sx2;
         Seg seg = make_seg(a, g, partials, counters, c.tiles);
+        seg.flags = tn.l2_prefetch;
         seg.stats_out = nullptr;   // patched per run for stats
         // tag for stats runs: remember which public segment this is (reuse chan_stride, unused by kernels)
         seg.chan_stride = (long long)i;
@@ -662,6 +665,7 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "max_unit_bytes") g_tuning.max_unit_bytes = v;
         else if (k == "interleave") g_tuning.interleave = v;
         else if (k == "pdl") g_tuning.pdl = v;
+        else if (k == "l2_prefetch") g_tuning.l2_prefetch = (v >= 0 && v <= 8) ? v : 0;
         else if (k == "whole_waves") g_tuning.whole_waves = v;
         else if (k == "column_path") g_tuning.column_path = v;
         else if (k == "col_variant") g_tuning.col_variant = (v >= 0 && v < kColVariants) ? v : 0;

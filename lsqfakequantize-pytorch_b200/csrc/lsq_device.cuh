@@ -90,7 +90,7 @@ struct Seg {
     int obs_zp_sym;        // zero point of the symmetric scheme (0, 128 or (qmin+qmax)//2)
     // integer export (lsq_export.cuh): y holds uint8 / int8 codes
     int code_signed;       // 1: int8 codes (qint8), 0: uint8 (quint8)
-    int reserved0;
+    int flags;             // L2-prefetch depth: this many of a thread's first units are prefetched before the dependency wait (Tuning::l2_prefetch, 0 = off)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -380,6 +380,11 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, double* sm /* [
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+// Non-binding L2 prefetch of the line a thread will load first, issued BEFORE griddepcontrol.wait: while the predecessor's tail
+// drains (DRAM otherwise idle) the kernel's first round of loads is already on its way into L2, so the ramp after the wait starts
+// from L2 latency instead of DRAM latency.  Harmless if the predecessor is still producing the data: L2 is the point of coherence,
+// a later write updates the prefetched line in place and the loads after the wait see it.
+__device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // A group may walk several CONSECUTIVE tiles (rows of the same weight tensor, as a rule), so
 // the descriptor look-up and staging are paid once per few rows, not once per row.
@@ -527,8 +532,19 @@ lsq_fwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
     const T* __restrict__ x2p = reinterpret_cast<const T*>(sg.x2);
     T* __restrict__ yp = reinterpret_cast<T*>(sg.y);
-    Walker w;
+    Walker w{};
     w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    if constexpr (VEC > 1) {
+        if (sg.flags) {
+            Walker pw = w;                        // a copy walks ahead; the real walker is untouched
+            for (int d = 0; d < sg.flags && pw.more(); d++) {
+                long long a0;
+                pw.next(a0);
+                l2_prefetch(reinterpret_cast<const char*>(xp) + a0 * UB);
+                if constexpr (ADD) l2_prefetch(reinterpret_cast<const char*>(x2p) + a0 * UB);
+            }
+        }
+    }
     pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, tl.pidx);
@@ -664,8 +680,20 @@ lsq_bwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ table
     const T* __restrict__ gp = reinterpret_cast<const T*>(sg.g);
     T* __restrict__ gxp = reinterpret_cast<T*>(sg.gx);
     const bool write_gx = gxp != nullptr;
-    Walker w;
+    Walker w{};
     w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+    if constexpr (VEC > 1) {
+        if (sg.flags) {
+            Walker pw = w;                        // a copy walks ahead; the real walker is untouched
+            for (int d = 0; d < sg.flags && pw.more(); d++) {
+                long long a0;
+                pw.next(a0);
+                l2_prefetch(reinterpret_cast<const char*>(xp) + a0 * UB);
+                l2_prefetch(reinterpret_cast<const char*>(gp) + a0 * UB);
+                if constexpr (ADD) l2_prefetch(reinterpret_cast<const char*>(x2p) + a0 * UB);
+            }
+        }
+    }
     pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, tl.pidx);
@@ -798,7 +826,7 @@ lsq_stats_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ tab
             s1 += (double)d; s2 += (double)__fmul_rn(d, d);
         }
     }
-    Walker w;
+    Walker w{};
     w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
     while (w.more()) {
         long long addr[UNROLL];
@@ -1214,6 +1242,7 @@ lsq_rowfwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ ta
     const char* px = reinterpret_cast<const char*>(xp + rg.e0 + rg.head) + lane * UB;
     char* py = reinterpret_cast<char*>(yp + rg.e0 + rg.head) + lane * UB;
     const long long pidx = sg->per_channel ? c : 0;
+    if (sg->flags && lane < units) l2_prefetch(px);
     pdl_wait();
     Chan ch;
     float sraw = 0.f, braw = 0.f;
@@ -1267,6 +1296,7 @@ lsq_rowbwd_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ ta
     const char* pg = reinterpret_cast<const char*>(sg->g) + row_off;
     char* pgx = sg->gx ? reinterpret_cast<char*>(sg->gx) + row_off : nullptr;
     const long long pidx = sg->per_channel ? c : 0;
+    if (sg->flags && lane < units) { l2_prefetch(px); l2_prefetch(pg); }
     pdl_wait();
     const float sraw = load_param(sg->scale, pidx, sg->pdt), braw = load_param(sg->shift, pidx, sg->pdt);
     Chan ch;
@@ -1338,6 +1368,7 @@ lsq_flatfwd_kernel(const __grid_constant__ Seg sg) {
     const char* px = reinterpret_cast<const char*>(sg.x) + u * UB;
     char* py = reinterpret_cast<char*>(sg.y) + u * UB;
     const long long sb = stride * UB;
+    for (int d = 0; d < sg.flags && u + d * stride < units; d++) l2_prefetch(px + d * sb);
     pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, 0);
@@ -1377,6 +1408,7 @@ lsq_flatbwd_kernel(const __grid_constant__ Seg sg) {
     const char* pg = reinterpret_cast<const char*>(sg.g) + u * UB;
     char* pgx = sg.gx ? reinterpret_cast<char*>(sg.gx) + u * UB : nullptr;
     const long long sb = stride * UB;
+    for (int d = 0; d < sg.flags && u + d * stride < units; d++) { l2_prefetch(px + d * sb); l2_prefetch(pg + d * sb); }
     pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, 0);
@@ -1461,7 +1493,7 @@ lsq_observe_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ t
             mn = nan_min(mn, v); mx = nan_max(mx, v);
         }
     }
-    Walker w;
+    Walker w{};
     w.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
     while (w.more()) {
         long long addr[UNROLL];

@@ -145,6 +145,7 @@ struct Tuning {
     int column_max_row_bytes = 512;   // rows shorter than this (or not 16 B multiples) take the column path
     int whole_waves = 1;        // round big-tensor tile counts to whole waves of resident CTAs
     int pdl = 1;                // launch with programmatic stream serialization (prologue overlaps predecessor's tail)
+    int l2_prefetch = 2;        // units per thread L2-prefetched before the dependency wait (row-tiled / flat / weight-row forward and backward); B200 step: 0 -> 6158, 1 -> 6231, 2 -> 6234, 4 -> 6238, 8 -> 6232 GB/s
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
     // single per-tensor launches in 32-byte aligned buffers: the lean kernels (bit-identical results).  1 = forward only (default),
     // 2 = forward and backward, 0 = off.  B200, bf16 sites: lean forward is faster alone (ncu: 120.7 vs 123.5 us on the largest

@@ -1,10 +1,10 @@
 #!/bin/bash
-# A/B of LSQB200_TUNE settings on the headline step: tools/ab_tune.sh "<spec A>" "<spec B>" [rounds]; alternates A, B, A, B ... on one box
+# several LSQB200_TUNE specs on the headline step, round-robin: tools/ab_multi.sh <rounds> "<spec>" "<spec>" ...
 set -u
-A=$1; B=$2; R=${3:-3}
+R=$1; shift
 Q="--no-e2e --no-cpu-baseline --no-fusion-mode --no-api-mode --no-configs --no-strong --steps 30"
 for r in $(seq $R); do
-  for spec in "$A" "$B"; do
+  for spec in "$@"; do
     LSQB200_TUNE="$spec" python bench.py $Q 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('spec=[$spec]', 'value', d['value'], 'ms', d['ms_per_step'], 'bwd', d['roofline']['achieved'], 'plan', d['plan_mode']['value'])"
   done
 done
