@@ -207,6 +207,7 @@ ColSeg make_colseg(const ColGeom& g, const void* x, const void* x2, void* y, con
     cs.qmin = (float)q->quant_min; cs.qmax = (float)q->quant_max; cs.tmin = (float)q->type_min; cs.tmax = (float)q->type_max;
     cs.tx = g.tx; cs.ty = g.ty; cs.pdt = pdt; cs.sym = q->sym;
     cs.total_ctas = (unsigned)(g.col_blocks * g.row_splits);
+    cs.l2_prefetch = tuning().l2_prefetch;
     return cs;
 }
 
@@ -763,7 +764,8 @@ int lsqb200_weight_init_stats(const void* w, float* scale_out, int64_t outer, in
     SegArgs a = seg_args(w, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, outer, C, inner, xdtype, DT_F32,
                          C > 1, &q);
     a.stats_out = scale_out;
-    const Seg seg = make_seg(a, g, partials, counters, 0);
+    Seg seg = make_seg(a, g, partials, counters, 0);
+    seg.flags = tuning().l2_prefetch;
     const bool rows = row_kernels_eligible(g, xdtype) && tuning().rowstats;
     // the row-entry kernels (variants >= 4) need a plan's table: single calls take the descriptor form
     KernelFn k = rows ? get_rowstats_kernel(xdtype, tuning().rowstats >= 4 ? 2 : tuning().rowstats) : get_stats_kernel(xdtype, g.nw, g.group);
@@ -799,6 +801,7 @@ int lsqb200_observe(const void* x, int64_t outer, int64_t C, int64_t inner, int 
     seg.obs_eps = (float)oa->eps;
     seg.obs_flags = (oa->symmetric ? 1 : 0) | (oa->moving_average ? 2 : 0);
     seg.obs_zp_sym = oa->zero_point_sym;
+    seg.flags = tuning().l2_prefetch;
     KernelFn k = get_observe_kernel(xdtype, g.nw, g.group);
     return launch(k, seg, nullptr, nullptr, 0, g.tiles, g.grid, (cudaStream_t)stream);
 }

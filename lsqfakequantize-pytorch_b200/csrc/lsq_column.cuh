@@ -38,6 +38,7 @@ struct ColSeg {
     int tx, ty;                // logical CTA shape: tx column units x ty rows, tx * ty == THREADS
     int pdt, sym, per_channel_unused;
     unsigned total_ctas;
+    int l2_prefetch;           // rows per thread L2-prefetched before the dependency wait (0 = off)
 };
 
 constexpr int kColThreads = 256;
@@ -147,6 +148,10 @@ lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
     const char* __restrict__ px = reinterpret_cast<const char*>(cs.x) + w.off;
     const char* __restrict__ px2 = ADD ? reinterpret_cast<const char*>(cs.x2) + w.off : nullptr;
     char* __restrict__ py = reinterpret_cast<char*>(cs.y) + w.off;
+    for (int r = 0; r < cs.l2_prefetch && r < w.cnt; r++) {      // first rows on their way into L2 while the predecessor drains
+        l2_prefetch(px + r * w.stride);
+        if constexpr (ADD) l2_prefetch(px2 + r * w.stride);
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     SlotParams<T, MODE, CNW> sp;
     if (!INIT) sp.load(cs, uc);
@@ -216,6 +221,15 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
     float accS[VEC], accB[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; k++) { accS[k] = 0.f; accB[k] = 0.f; sacc[0][k][threadIdx.x] = 0.0; sacc[1][k][threadIdx.x] = 0.0; }
+    if (active && cs.l2_prefetch) {               // first rows on their way into L2 while the predecessor drains
+        ColWalk pw;
+        pw.init(cs, uc, ty, UB);
+        for (int r = 0; r < cs.l2_prefetch && r < pw.cnt; r++) {
+            l2_prefetch(reinterpret_cast<const char*>(cs.x) + pw.off + r * pw.stride);
+            l2_prefetch(reinterpret_cast<const char*>(cs.g) + pw.off + r * pw.stride);
+            if constexpr (ADD) l2_prefetch(reinterpret_cast<const char*>(cs.x2) + pw.off + r * pw.stride);
+        }
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (active) {
         ColWalk w;

@@ -1017,6 +1017,7 @@ lsq_rowstats3_kernel(const __grid_constant__ Seg single, const Seg* __restrict__
         const int units = (inner - head) / VEC;
         const int tail = inner - head - units * VEC;
         const char* p = reinterpret_cast<const char*>(rowp + head) + lane * UB;
+        if (single.flags && lane < units) l2_prefetch(p);
         pdl_wait();
         Raw<NW> r[UNROLL];
         if (units > 0) {
@@ -1477,14 +1478,26 @@ lsq_observe_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ t
     __shared__ float red[64];
     __shared__ int last_flag[GROUPS];
     const int grp = threadIdx.x / G, tg = threadIdx.x % G;
-    pdl_prologue();
+    pdl_trigger();
     int staged = -2;
     const long long gtile = (long long)blockIdx.x * GROUPS + grp;
     if (gtile >= total_tiles) return;
-    stage_segment<G, THREADS>(single, table, tile_seg, nseg, gtile, &smem_seg[grp], staged);
+    stage_segment<G, THREADS>(single, table, tile_seg, nseg, gtile, &smem_seg[grp], staged);   // descriptors are launch constants
     const Seg& sg = smem_seg[grp];
     const TileCtx tl = make_tile<VEC>(sg, gtile);
     const T* __restrict__ xp = reinterpret_cast<const T*>(sg.x);
+    if constexpr (VEC > 1) {
+        if (sg.flags) {                           // first units on their way into L2 while the predecessor drains
+            Walker pw{};
+            pw.init<G>(sg, tl.u0, tl.u1, tl.base_unit, tg);
+            for (int d = 0; d < sg.flags && pw.more(); d++) {
+                long long a0;
+                pw.next(a0);
+                l2_prefetch(reinterpret_cast<const char*>(xp) + a0 * UB);
+            }
+        }
+    }
+    pdl_wait();
     float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
     if constexpr (VEC > 1) {
         for (long long i = tg; i < tl.peel_n0 + tl.peel_n1; i += G) {
