@@ -495,7 +495,7 @@ def run_b200(args):
                        "parallelism": f"dp{world}"},
             "per_gpu_GBps": round(value / world, 1), "pct_of_hbm_peak_per_gpu": round(100 * value / world / peak, 2),
             "pct_of_8TBps_spec": round(100 * value / world / 8000.0, 2),
-            "roofline": {"bound": "hbm", "kernel": "lsq_bwd_kernel<bf16> (per-tensor backward, 71 launches/step)",
+            "roofline": {"bound": "hbm", "kernel": "lsq_flatbwd_kernel<bf16> (per-tensor backward, 71 launches/step)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": bwd_bytes, "avg_ms_per_step": round(bwd_ms, 4)},
@@ -800,7 +800,7 @@ def run_strong_line(args, torch, dist, lib, flat, wplan, ws, sp, stream, dev, wo
                                        "(71 bf16 per-tensor activation sites + 54 fp32 per-channel weights, fwd+bwd, flat-grad all-reduce when N>1)",
                            "global_batch": 2048, "batch_per_gpu": r["batch_per_gpu"], "l2": r["arena"], "parallelism": f"dp{world}"},
                 "per_gpu_GBps": r["per_gpu_GBps"], "pct_of_hbm_peak_per_gpu": round(100 * r["frac_of_measured_peak_per_gpu"], 2),
-                "roofline": {"bound": "hbm", "kernel": "lsq_bwd_kernel<bf16> (per-tensor backward, 71 launches/step)",
+                "roofline": {"bound": "hbm", "kernel": "lsq_flatbwd_kernel<bf16> (per-tensor backward, 71 launches/step)",
                              "achieved": r["bwd_bf16_achieved_GBps"], "peak": peak, "unit": "GB/s",
                              "frac": round(r["bwd_bf16_achieved_GBps"] / peak, 4), "traffic": None},
                 "dp_check": r["dp_check"], "cpu_baseline": None, "e2e": None, "gpu_launches": r["launches_per_step"] * r["steps"],

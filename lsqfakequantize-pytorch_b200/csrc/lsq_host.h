@@ -147,12 +147,14 @@ struct Tuning {
     int pdl = 1;                // launch with programmatic stream serialization (prologue overlaps predecessor's tail)
     int l2_prefetch = 2;        // units per thread L2-prefetched before the dependency wait (row-tiled / flat / weight-row forward and backward); B200 step: 0 -> 6158, 1 -> 6231, 2 -> 6234, 4 -> 6238, 8 -> 6232 GB/s
     int max_unit_bytes = 32;    // 32 -> LDG.E.256 / STG.E.256 (sm_100), 16 -> 128-bit accesses
-    // single per-tensor launches in 32-byte aligned buffers: the lean kernels (bit-identical results).  1 = forward only (default),
-    // 2 = forward and backward, 0 = off.  B200, bf16 sites: lean forward is faster alone (ncu: 120.7 vs 123.5 us on the largest
-    // site, 8.5 vs 10.0 on the smallest) and in a stream (123.6 vs 127.0); lean backward is faster alone (186.4 vs 190.7) but
-    // SLOWER back to back under programmatic dependent launch (193.6 vs 188.0 per launch) - the general kernel's long set-up
-    // runs before its griddepcontrol.wait and overlaps the predecessor's reduction tail - so the backward stays general
-    int flatkernels = 1;
+    // single per-tensor launches in 32-byte aligned buffers: the lean kernels (bit-identical results).  1 = forward only,
+    // 2 = forward and backward (default since round 2), 0 = off.  B200, bf16 sites: lean forward is faster alone (ncu: 120.7 vs
+    // 123.5 us on the largest site, 8.5 vs 10.0 on the smallest) and in a stream (123.6 vs 127.0); the lean backward is faster alone
+    // (186.4 vs 190.7) but was SLOWER back to back under programmatic dependent launch in round 1 (193.6 vs 188.0 per launch: the
+    // general kernel's long set-up runs before its griddepcontrol.wait and overlaps the predecessor's reduction tail).  With the L2
+    // prefetch of the first units in front of the wait (l2_prefetch) the lean backward has useful work for that window too:
+    // 71 + 54-site step 6193 GB/s (1), 6213 (2), 6203 (0); bf16 backward in the step 6115 / 6147 / 6105 GB/s.
+    int flatkernels = 2;
     int rowkernels = 1;         // forward / backward over aligned weight rows: the lean warp-per-row kernels (0: the general warp-group kernels)
     int rowstats = 4;           // mu +- 3 sigma over aligned weight rows (kern_stats.cu): 1 / 2 / 3 descriptor form (x4 / x2 / x1 units in flight), 4 / 5 / 6 row-entry form (plans; default 4: x2, 6 CTAs/SM), 7 bulk-copy ring; 0: the general kernel
                                 // 54 ResNet-50 weights under ncu on B200: general kernel 34.5 us, variant 1 28.7, 2 25.2, 3 26.3

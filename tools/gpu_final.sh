@@ -14,7 +14,7 @@ cap() { name=$1; rx=$2; skip=$3; shift 3
     ncu --set full --clock-control none --import-source on --kernel-name regex:$rx --launch-skip $skip --launch-count 1 -f -o /tmp/$name "$@" > $out/$name.log 2>&1
     ncu -i /tmp/$name.ncu-rep --page raw --csv > $out/$name.raw.csv 2>/dev/null
     rm -f /tmp/$name.ncu-rep; }
-cap ${tag}_prof_bwd lsq_bwd_kernel 69 python bench.py --steps 1 --warmup 3 $Q
+cap ${tag}_prof_bwd lsq_flatbwd_kernel 69 python bench.py --steps 1 --warmup 3 $Q
 cap ${tag}_prof_fwd lsq_flatfwd_kernel 1 python bench.py --steps 1 --warmup 3 $Q
 python tools/host_overhead.py > $out/${tag}_host.txt 2>&1
 python tools/host_overhead.py ref >> $out/${tag}_host.txt 2>&1
