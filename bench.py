@@ -426,7 +426,10 @@ def run_b200(args):
     #      tests/test_gpu_add.py); the figure is ms per step over ALL sites, N = 1 only.
     fusion_mode = None
     if world == 1 and not args.no_fusion_mode:
-        fusion_mode = run_fusion_mode(args, torch, lib, acts, flat, ws, sp, stream, wplan, qa, BF16, F32, dev, gen)
+        try:
+            fusion_mode = run_fusion_mode(args, torch, lib, acts, flat, ws, sp, stream, wplan, qa, BF16, F32, dev, gen)
+        except Exception as exc:       # an extra measurement, never a reason to lose the line
+            fusion_mode = {"error": repr(exc)}
 
     # ---- every BASELINE config as its own measurement (L2 flushed between iterations where the working set is small)
     peaks = {}
@@ -459,7 +462,12 @@ def run_b200(args):
     # ---- end to end through the public op with HOST buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites)
+        try:
+            e2e = run_e2e(args, torch, lsq, dev, B, world, dist, flat, wsites)
+        except Exception as exc:
+            if world > 1:              # a rank that dropped out of the e2e collectives would hang the others: fail loudly instead
+                raise
+            e2e = {"value": None, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(exc)}
 
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, torch copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     traffic = None
