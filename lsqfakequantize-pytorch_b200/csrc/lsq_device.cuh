@@ -1369,7 +1369,7 @@ lsq_flatfwd_kernel(const __grid_constant__ Seg sg) {
     const char* px = reinterpret_cast<const char*>(sg.x) + u * UB;
     char* py = reinterpret_cast<char*>(sg.y) + u * UB;
     const long long sb = stride * UB;
-    for (int d = 0; d < sg.flags && u + d * stride < units; d++) l2_prefetch(px + d * sb);
+    if (sg.flags && u < units) l2_prefetch(px);     // one unit: the next one is a whole grid stride away (depth 1 / 2 / 3: 6207 / 6197 / 6153 GB/s on the step)
     pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, 0);
@@ -1409,7 +1409,7 @@ lsq_flatbwd_kernel(const __grid_constant__ Seg sg) {
     const char* pg = reinterpret_cast<const char*>(sg.g) + u * UB;
     char* pgx = sg.gx ? reinterpret_cast<char*>(sg.gx) + u * UB : nullptr;
     const long long sb = stride * UB;
-    for (int d = 0; d < sg.flags && u + d * stride < units; d++) { l2_prefetch(px + d * sb); l2_prefetch(pg + d * sb); }
+    if (sg.flags && u < units) { l2_prefetch(px); l2_prefetch(pg); }   // one unit per operand, see lsq_flatfwd_kernel
     pdl_wait();                                   // first touch of tensor / parameter memory is below
     LazyChan<MODE> lch;
     lch.issue(sg, 0);
