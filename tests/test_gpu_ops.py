@@ -516,3 +516,32 @@ def test_weight_init_stats_kernel_variants_bit_identical():
             assert torch.equal(single.view(torch.int32), outs[2].view(torch.int32)), dtype
     finally:
         lib.lsqb200_set_tuning(b"")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_input_without_grad_skips_grad_x_but_not_the_parameter_sums(dtype):
+    """The C++ autograd layer hands the kernels a NULL grad_x when the input needs no gradient (a network's first quantizer, frozen
+    features): two reads, no write.  The parameter gradients must be exactly those of the call that also produces grad_x, per tensor,
+    per channel (row-tiled and column layouts) and behind a fused ReLU; layouts that are dense but not contiguous included."""
+    from torchlsq.functional import lsq, lsq_relu
+    gen = torch.Generator().manual_seed(11)
+    cases = [((4, 16, 28, 28), None), ((4, 16, 28, 28), 1), ((8, 32, 7, 7), 1), ((64, 24), 1), ((32, 16, 3, 3), 0)]
+    for shape, axis in cases:
+        for fn in (lsq, lsq_relu):
+            C = 1 if axis is None else shape[axis]
+            x0 = torch.randn(*shape, generator=gen).to(dtype).to(U.DEV)
+            if len(shape) == 4 and axis == 1:
+                x0 = x0.contiguous(memory_format=torch.channels_last)      # dense, not contiguous: processed in memory order
+            g = torch.randn(*shape, generator=gen).to(dtype).to(U.DEV)
+            grads = []
+            for need_x in (True, False):
+                x = x0.clone().requires_grad_(need_x)
+                s = (0.02 + 0.02 * torch.rand(C, generator=torch.Generator().manual_seed(3))).to(U.DEV).requires_grad_(True)
+                b = (-torch.rand(C, generator=torch.Generator().manual_seed(4))).to(U.DEV).requires_grad_(True)
+                y = fn(x, s, b, 0, 127, 0, 255, axis=0 if axis is None else axis, is_perchannel=axis is not None)
+                y.backward(g)
+                assert (x.grad is not None) == need_x
+                grads.append((y.detach(), s.grad.clone(), b.grad.clone()))
+            assert torch.equal(grads[0][0], grads[1][0])
+            # same kernel, same reduction order: bit-identical unless the layout takes the column path (fp64 atomics in arrival order)
+            assert torch.allclose(grads[0][1], grads[1][1], rtol=1e-6, atol=0) and torch.allclose(grads[0][2], grads[1][2], rtol=1e-6, atol=0), (shape, axis, fn.__name__)
