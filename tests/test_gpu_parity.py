@@ -545,3 +545,37 @@ def test_config3_largest_site_full_size_vs_oracle():
         del gx, ogx
         U.assert_grads_close(gs, ogs, ms, 1e-6, f"config3 largest site gscale ({what})")
         U.assert_grads_close(gb, ogb, mb, 1e-6, f"config3 largest site gshift ({what})")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_back_to_back_producer_consumer_chain_under_pdl_and_prefetch(dtype):
+    """Kernels are launched with programmatic dependent launch and L2-prefetch their first units BEFORE griddepcontrol.wait.  A chain
+    in which every launch consumes what the previous one is still writing (forward -> forward on its output -> backward with that
+    output as upstream gradient, ping-pong buffers, no host sync in between) must give bit for bit what the same chain gives with a
+    device synchronisation after every launch: the prefetch is non-binding and L2 is the point of coherence."""
+    n = 8 * 1024 * 1024 + 24
+    gen = torch.Generator(device=U.DEV).manual_seed(21)
+    x0 = torch.empty(n, device=U.DEV).normal_(0, 1, generator=gen).to(dtype)
+    s, b = _params([0.05], [-1.3])
+    q = U.qa()
+
+    def chain(sync):
+        out = []
+        cur = x0
+        for i in range(12):
+            y = U.fwd(cur, s, b, q)
+            if sync:
+                torch.cuda.synchronize()
+            gx, gs, gb = U.bwd(y, cur, s, b, q)          # upstream gradient = the tensor the previous launch just wrote
+            if sync:
+                torch.cuda.synchronize()
+            out.append((gs.clone(), gb.clone()))
+            cur = (gx * 0.5 + y).to(dtype) if i % 3 == 2 else y          # an ATen kernel in the chain now and then
+        torch.cuda.synchronize()
+        return cur, out
+
+    a_cur, a_out = chain(False)
+    b_cur, b_out = chain(True)
+    assert U.same_bits(a_cur, O.to_bits(b_cur)[0])
+    for (gs1, gb1), (gs2, gb2) in zip(a_out, b_out):
+        assert torch.equal(gs1, gs2) and torch.equal(gb1, gb2)
