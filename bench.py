@@ -685,6 +685,24 @@ def run_configs(args, torch, lib, acts, wplan, ws, sp, stream, scales, dev, peak
                             lib.lsqb200_bwd_channel(g4.data_ptr() + o, x4.data_ptr() + o, gx4.data_ptr() + o, sc.data_ptr(), bc.data_ptr(),
                                                     gsc.data_ptr(), gbc.data_ptr(), outer, cc, hw, 1, 0, q, ws.data_ptr(), ws.numel(), sp))
         report(name, 5 * 2 * nn_, _timed_rotating(torch, [c4(k) for k in range(nset)], iters, stream), sets=nset, launches=2)
+    # dtype matrix of the per-tensor kernels on one large site (205 MB per buffer, 1 GB working set: far above L2): fp32, fp16 and
+    # bf16 tensors with fp32 parameters, and the reference-exact all-fp16 contract (c10::Half: a rounding after every operator)
+    nbig = 256 * 128 * 56 * 56
+    for name, tdt, code, pcode in (("per_tensor_205MB_fp32", torch.float32, 0, 0), ("per_tensor_205MB_fp16_fp32params", torch.float16, 1, 0),
+                                   ("per_tensor_205MB_fp16_exact_fp16params", torch.float16, 1, 1), ("per_tensor_205MB_bf16_fp32params", torch.bfloat16, 2, 0)):
+        es = 4 if tdt == torch.float32 else 2
+        m = nbig // (2 if es == 4 else 1)             # the four fp16 buffers hold 205.5 M halves = 102.8 M floats
+        xb, gb_, yb, gxb = (t.view(tdt)[:m] for t in (x4, g4, y4, gx4))
+        pdt = torch.float16 if pcode == 1 else torch.float32
+        sp_, bp_ = torch.tensor([0.03], device=dev, dtype=pdt), torch.tensor([-1.7], device=dev, dtype=pdt)
+        gsp, gbp = torch.empty(1, device=dev, dtype=pdt), torch.empty(1, device=dev, dtype=pdt)
+        qd = _cabi.qargs(0, 127, 0, 255, code != 1 or pcode != 1, 1.0, False, False, False)      # all-fp16: grad scaling off
+
+        def cd():
+            lib.lsqb200_fwd_tensor(xb.data_ptr(), yb.data_ptr(), sp_.data_ptr(), bp_.data_ptr(), m, code, pcode, qd, sp)
+            lib.lsqb200_bwd_tensor(gb_.data_ptr(), xb.data_ptr(), gxb.data_ptr(), sp_.data_ptr(), bp_.data_ptr(), gsp.data_ptr(), gbp.data_ptr(),
+                                   m, code, pcode, qd, ws.data_ptr(), ws.numel(), sp)
+        report(name, 5 * es * m, _timed_rotating(torch, [cd], max(5, iters // 2), stream), sets=1, launches=2, elements=m)
     # observer-mode init step on a 411 MB bf16 activation: x4 / g4 / y4 / gx4 as four inputs
     import warnings
     from torchlsq.quantized.modules.observers import observer_step
