@@ -167,7 +167,7 @@ int occupancy_of(const void* fn, int threads) {
 ColGeom plan_column(int64_t outer, int64_t C, int64_t inner, int xdt, int align_bytes, const Tuning& tn, int occ, bool backward,
                     bool relu = false) {
     ColGeom g{};
-    const int ub = kColVariantNW[relu ? kColVariantRelu : tn.col_variant] * 4;
+    const int ub = kColVariantNW[relu ? kColVariantRelu : (backward ? tn.col_variant : tn.col_variant_fwd)] * 4;
     const int es = elem_size(xdt), vec = ub / es;
     const long long L = C * inner;
     g.ok = tn.column_path && outer > 1 && C > 1 && C <= kMaxColumnChannels && L < (1LL << 31) && align_bytes % 16 == 0 && (L * es) % 16 == 0 &&
@@ -251,7 +251,7 @@ int forward_common(const void* x, const void* x2, void* y, const void* scale, co
     if (!x || !y || !scale || !shift) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
     if (xdt == DT_F64 && common_alignment({x, y, scale, shift}) < 8) return fail(LSQB200_ERR_ARG, "float64 tensors must be 8-byte aligned");
     if (per_channel && xdt != DT_F64) {
-        ColKernelFn ck = get_col_fwd_kernel(xdt, mode, q->init_mode != 0, tuning().col_variant);
+        ColKernelFn ck = get_col_fwd_kernel(xdt, mode, q->init_mode != 0, tuning().col_variant_fwd);
         const ColGeom cg = plan_column(outer, C, inner, xdt, common_alignment({x, x2, y}), tuning(), occupancy_of((const void*)ck, kColThreads), false, mode_relu(mode) || mode_add(mode));
         if (cg.ok) {
             const ColSeg cs = make_colseg(cg, x, x2, y, nullptr, nullptr, scale, shift, nullptr, nullptr, outer, C, inner, pdt, q, nullptr);
@@ -669,7 +669,9 @@ int lsqb200_set_tuning(const char* spec) {
         else if (k == "l2_prefetch") g_tuning.l2_prefetch = (v >= 0 && v <= 8) ? v : 0;
         else if (k == "whole_waves") g_tuning.whole_waves = v;
         else if (k == "column_path") g_tuning.column_path = v;
-        else if (k == "col_variant") g_tuning.col_variant = (v >= 0 && v < kColVariants) ? v : 0;
+        else if (k == "col_variant") g_tuning.col_variant = g_tuning.col_variant_fwd = (v >= 0 && v < kColVariants) ? v : 0;   // both directions
+        else if (k == "col_variant_fwd") g_tuning.col_variant_fwd = (v >= 0 && v < kColVariants) ? v : 0;
+        else if (k == "col_variant_bwd") g_tuning.col_variant = (v >= 0 && v < kColVariants) ? v : 0;
         else if (k == "col_waves") g_tuning.col_waves = v > 0 ? v : 2;
         else if (k == "col_waves_bwd") g_tuning.col_waves_bwd = v > 0 ? v : 1;
         else if (k == "col_tma") g_tuning.col_tma = (v >= 0 && v <= 3) ? v : 0;

@@ -138,7 +138,8 @@ struct Tuning {
     int min_iters = 1;          // never split below min_iters full group iterations
     int interleave = 1;         // 1: interleave the splits of a channel (grid-stride style), 0: contiguous slices
     int column_path = 1;        // short channel rows (channels-last, 7x7 / 14x14 maps) use the column-layout kernels
-    int col_variant = 1;        // column kernels: 0 = 128-bit units x2 rows, 1 = x4 rows (default, r1 sweep), 2 = 64-bit units x4 rows, 3 = x8 rows
+    int col_variant = 1;        // column BACKWARD: 0 = 128-bit units x2 rows, 1 = x4 rows (default, r1 + r2 sweeps), 2 = 64-bit units x4 rows, 3 = x8 rows
+    int col_variant_fwd = 2;    // column FORWARD: 64-bit units x4 rows at 6 CTAs/SM (r2 sweep: +4-5 % over variant 1 on 7x7 / 14x14 / channels-last; the backward loses with it)
     int col_waves = 2;          // column forward: CTAs <= col_waves * sm_count * (resident CTAs/SM of the kernel), rounded DOWN to whole waves
     int col_tma = 0;            // column backward staged by the bulk-copy engine (lsq_col_bwd_tma_kernel): 0 off, 1 = 4 rows x 3 stages, 2 = 2 x 4, 3 = 8 x 3
     int col_waves_bwd = 1;      // column backward: one wave (per-thread set-up and the per-CTA atomics are paid once per row split; s6 sweep)
