@@ -541,9 +541,8 @@ def run_dp_check(torch, dist, flat, world, fwd_calls, bwd_calls, fwd_t, bwd_t, w
         dist.all_gather(gathered, local)
         flat.all_reduce()
         torch.cuda.synchronize()
-        stack = torch.stack([t.double() for t in gathered])
-        want = stack.sum(0)
-        bound = 1e-6 * want.abs() + world * 2.0 ** -24 * stack.abs().sum(0)
+        from torchlsq.dp import allreduce_bound
+        want, bound = allreduce_bound(gathered)
         err = (flat.flat.double() - want).abs()
         ratio = (err / bound.clamp_min(1e-300)).max().item()
         ok = torch.tensor([1 if (ratio <= 1.0 and bool(torch.isfinite(flat.flat).all().item())) else 0], device=local.device)

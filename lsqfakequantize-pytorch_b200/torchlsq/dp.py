@@ -216,6 +216,19 @@ def shard_batch(n: int, rank: int, world: int) -> Tuple[int, int]:
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def allreduce_bound(per_rank: List[torch.Tensor], rel: float = 1e-6) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(want, bound) for checking an fp32 SUM-all-reduce of W per-rank buffers element by element:
+    want = the fp64 sum over ranks, bound = rel * |want| + W * 2^-24 * sum_r |shard_r|.
+
+    An fp32 sum of W addends in ANY order is within (W - 1) * 2^-24 * sum_r |shard_r| of the exact sum; relative to the RESULT
+    the error is unbounded once the shards cancel, which is why a plain `|got - want| / |want| < 1e-6` check (round 1) holds
+    for W = 2 - one correctly rounded addition - and fails by construction for W >= 4."""
+    stack = torch.stack([t.double() for t in per_rank])
+    want = stack.sum(0)
+    bound = rel * want.abs() + len(per_rank) * 2.0 ** -24 * stack.abs().sum(0)
+    return want, bound
+
+
 def expected_allreduced(per_rank: List[torch.Tensor], average: bool = False) -> torch.Tensor:
     """Reference semantics of the all-reduced buffer: sum over ranks (/ world if average)."""
     out = torch.stack([t.double() for t in per_rank]).sum(0)
