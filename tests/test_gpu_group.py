@@ -174,3 +174,37 @@ def _grouped_training_body(LSQFakeQuantizer, group_weight_quantizers, calls):
     handle.remove()
     with torch.no_grad():
         assert torch.equal(plain(x0), grouped(x0))
+
+
+def test_group_per_tensor_sites_and_awkward_upstream_grads():
+    """Per-tensor sites (one scale / shift element each) in a group, and upstream gradients autograd may hand over in any form:
+    a misaligned view, an expanded scalar (y.sum().backward()), a missing one (an output nobody used).  The group copies what the
+    kernels cannot read in place and must still match per-site calls bit for bit."""
+    from torchlsq.functional import lsq
+    from torchlsq.multi import LSQGroup
+    gen = torch.Generator(device=DEV).manual_seed(9)
+    shapes = [(4, 16, 14, 14), (1000,), (3, 5, 7), (8, 64)]
+    for dtype in (torch.float32, torch.bfloat16):
+        xs = [torch.randn(s, device=DEV, generator=gen).to(dtype).requires_grad_(True) for s in shapes]
+        sc = [torch.tensor([0.03 + 0.01 * i], device=DEV, requires_grad=True) for i in range(len(shapes))]
+        sh = [torch.tensor([-0.5 * i], device=DEV, requires_grad=True) for i in range(len(shapes))]
+        xs2, sc2, sh2 = ([t.detach().clone().requires_grad_(True) for t in ts] for ts in (xs, sc, sh))
+        group = LSQGroup(xs, sc, sh, 0, 127, 0, 255, is_affine=True, is_perchannel=False)
+        ys = group()
+        ys2 = [lsq(x, s, b, 0, 127, 0, 255) for x, s, b in zip(xs2, sc2, sh2)]
+        big = torch.randn(shapes[0][0] * shapes[0][1] * 196 + 1, device=DEV, generator=gen).to(dtype)
+        g0 = big[1:].view(shapes[0])                                   # not 32-byte aligned
+        g1 = torch.ones((), device=DEV, dtype=dtype).expand(shapes[1])   # what sum().backward() produces
+        g2 = torch.randn(shapes[2], device=DEV, generator=gen).to(dtype)
+        # output 3 gets no gradient at all
+        torch.autograd.backward([ys[0], ys[1], ys[2]], [g0, g1, g2])
+        torch.autograd.backward([ys2[0], ys2[1], ys2[2]], [g0, g1, g2])
+        for i in range(3):
+            assert torch.equal(ys[i], ys2[i])
+            assert torch.equal(xs[i].grad, xs2[i].grad), (dtype, i)
+            # a plan may cut a per-tensor site into other tiles than a single launch does: same terms, another fixed fp64 order
+            assert torch.allclose(sc[i].grad, sc2[i].grad, rtol=1e-6, atol=0) and torch.allclose(sh[i].grad, sh2[i].grad, rtol=1e-6, atol=0), \
+                (dtype, i, sc[i].grad, sc2[i].grad, sh[i].grad, sh2[i].grad)
+        assert torch.equal(ys[3], ys2[3])
+        assert float(xs[3].grad.abs().sum()) == 0.0 and float(sc[3].grad.abs().sum()) == 0.0       # zeros for the unused output
+        group.close()
