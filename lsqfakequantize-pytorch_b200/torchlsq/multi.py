@@ -165,7 +165,10 @@ class LSQGroup:
     and the autograd engine) per site.  `group()` returns the list of fake-quantised tensors, differentiable with respect
     to every x, scale and shift: ONE autograd node (`torch.ops.torchlsq.lsq_group`, csrc/torch_binding.cpp) whose backward
     runs when autograd has the gradient of every output and hands back every grad_x / grad_scale / grad_shift as views of
-    three flat buffers (AccumulateGrad takes them over without a copy).  Bit-identical to n `torchlsq.functional.lsq` calls.
+    three flat buffers (AccumulateGrad takes them over without a copy).  Outputs and grad_x are bit-identical to n
+    `torchlsq.functional.lsq` calls; so are grad_scale / grad_shift of weight rows (same kernels, same order), while a per-tensor
+    site may be cut into other tiles inside a plan than by a single launch - the same terms summed in another fixed fp64 order,
+    i.e. equal to ~1e-15 before the final rounding.
     All sites share dtype, device and the scalar arguments below; x_i must be contiguous.
 
     The plan (device-side descriptor table) is built at the first call and rebuilt only when an input's storage moves; the
