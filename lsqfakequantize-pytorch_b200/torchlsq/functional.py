@@ -7,6 +7,16 @@ from .extension import _assert_has_ops
 
 
 Tensor = torch.Tensor
+_ops = {}
+
+
+def _op(name):
+    """The resolved overload (`torch.ops.torchlsq.<name>.default`): skips the packet's overload resolution on every call."""
+    f = _ops.get(name)
+    if f is None:
+        _assert_has_ops()
+        f = _ops[name] = getattr(torch.ops.torchlsq, name).default
+    return f
 
 
 def lsq(x: Tensor, scale: Tensor, shift: Tensor,
@@ -48,15 +58,14 @@ def lsq(x: Tensor, scale: Tensor, shift: Tensor,
         init_mode: learned initialisation - output is x itself, the input gradient passes
             through, and the parameters descend on ||y - x||^2.
     """
-    _assert_has_ops()
     if not is_affine:
         assert quant_min <= 0 <= quant_max, 'quantization range must be covered 0 in symmetric quantization'
     type_min = quant_min if type_min is None else type_min
     type_max = quant_max if type_max is None else type_max
 
-    return torch.ops.torchlsq.lsq(x, scale, shift, quant_min, quant_max, type_min, type_max,
-                                  axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel,
-                                  eval_mode, init_mode)
+    return _op("lsq")(x, scale, shift, quant_min, quant_max, type_min, type_max,
+                      axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel,
+                      eval_mode, init_mode)
 
 
 _ARGS_DOC = """Arguments after the tensors as in `lsq`.  Inputs: CUDA float32 / float16 / bfloat16 with float32 scale / shift
@@ -65,13 +74,12 @@ _ARGS_DOC = """Arguments after the tensors as in `lsq`.  Inputs: CUDA float32 / 
 
 def _pre(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max, axis, use_grad_scaling, grad_scaler,
          is_affine, is_perchannel, eval_mode, init_mode):
-    _assert_has_ops()
     if not is_affine:
         assert quant_min <= 0 <= quant_max, 'quantization range must be covered 0 in symmetric quantization'
     type_min = quant_min if type_min is None else type_min
     type_max = quant_max if type_max is None else type_max
-    return torch.ops.torchlsq.lsq_pre(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max,
-                                      axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel, eval_mode, init_mode)
+    return _op("lsq_pre")(prologue, x, x2, scale, shift, quant_min, quant_max, type_min, type_max,
+                          axis, use_grad_scaling, grad_scaler, is_affine, is_perchannel, eval_mode, init_mode)
 
 
 def lsq_relu(x: Tensor, scale: Tensor, shift: Tensor, quant_min: int = 0, quant_max: int = 255, type_min: int = None,
