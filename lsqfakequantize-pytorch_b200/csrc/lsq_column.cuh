@@ -42,6 +42,20 @@ struct ColSeg {
 };
 
 constexpr int kColThreads = 256;
+#ifndef LSQ_COL_EARLY_LOADS
+#define LSQ_COL_EARLY_LOADS 1
+#endif
+
+// diagnostic build (-DLSQ_COL_TRACE): per-CTA globaltimer stamps + SM id into the partials region of the workspace (tools/coltrace.py)
+#ifdef LSQ_COL_TRACE
+#define LSQ_TRACE(i) do { if (threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(cs.counter) + 16384)[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = t_; } } while (0)
+#define LSQ_TRACE_SM() do { if (threadIdx.x == 0) { unsigned s_; asm volatile("mov.u32 %0, %%smid;" : "=r"(s_)); \
+    reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(cs.counter) + 16384)[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + 7] = s_; } } while (0)
+#else
+#define LSQ_TRACE(i) do {} while (0)
+#define LSQ_TRACE_SM() do {} while (0)
+#endif
 
 // CNW: 32-bit words per column unit (4 = 128-bit, 2 = 64-bit accesses); fewer slots per thread
 // mean fewer registers (more resident CTAs) at the price of narrower accesses
@@ -92,6 +106,16 @@ struct SlotParams {
         return c;
     }
 };
+
+// The scale / shift entries of a thread's first channel on their way into L2 before the dependency wait: a prefetch binds no value,
+// so whatever the predecessor still writes is what the loads behind the wait see, and the parameter request at the front of the
+// kernel is an L2 hit instead of a DRAM round trip shared by every CTA of the launch.
+__device__ __forceinline__ void prefetch_params(const ColSeg& cs, long long elem_col) {
+    const unsigned c = (unsigned)elem_col / (unsigned)cs.inner;
+    const unsigned ps = cs.pdt == DT_F32 ? 4u : 2u;
+    l2_prefetch(reinterpret_cast<const char*>(cs.scale) + (size_t)c * ps);
+    l2_prefetch(reinterpret_cast<const char*>(cs.shift) + (size_t)c * ps);
+}
 
 // rows this thread visits inside its row split, and the byte offset of the first one (ty is a power of two)
 struct ColWalk {
@@ -152,18 +176,26 @@ lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
         l2_prefetch(px + r * w.stride);
         if constexpr (ADD) l2_prefetch(px2 + r * w.stride);
     }
+    if (!INIT && cs.l2_prefetch) prefetch_params(cs, uc * VEC);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    SlotParams<T, MODE, CNW> sp;
-    if (!INIT) sp.load(cs, uc);
     int cnt = w.cnt;
-    // whole groups of kColUnroll rows: unconditional loads and stores
-    for (; cnt >= kColUnroll; cnt -= kColUnroll) {
-        Raw<NW> xr[kColUnroll], x2r[ADD ? kColUnroll : 1];
+    Raw<NW> xr[kColUnroll], x2r[ADD ? kColUnroll : 1];
+    auto load_group = [&]() {
 #pragma unroll
         for (int r = 0; r < kColUnroll; r++) {
             xr[r] = ld_unit<LD, NW>(px + r * w.stride);
             if constexpr (ADD) x2r[r] = ld_unit<LD, NW>(px2 + r * w.stride);
         }
+    };
+    // the first group's loads are in flight before the parameters are requested: one memory round trip at the front, not two
+    // (16-bit tensors: +4 % on 7x7 maps; fp32 units leave too few registers at 6 CTAs/SM and lose 3-5 %, so they keep the plain order)
+    const bool pre = LSQ_COL_EARLY_LOADS && sizeof(T) == 2 && !INIT && cnt >= kColUnroll;
+    if (pre) load_group();
+    SlotParams<T, MODE, CNW> sp;
+    if (!INIT) sp.load(cs, uc);
+    // whole groups of kColUnroll rows: unconditional loads and stores
+    for (bool first = pre; cnt >= kColUnroll; cnt -= kColUnroll, first = false) {
+        if (!first) load_group();
 #pragma unroll
         for (int r = 0; r < kColUnroll; r++) {
             if (RAWCOPY) { st_unit<ST, NW>(py + r * w.stride, xr[r]); continue; }
@@ -183,11 +215,11 @@ lsq_col_fwd_kernel(const __grid_constant__ ColSeg cs) {
         if constexpr (ADD) px2 += kColUnroll * w.stride;
     }
     for (; cnt > 0; cnt--) {
-        const Raw<NW> xr = ld_unit<LD, NW>(px);
-        if (RAWCOPY) st_unit<ST, NW>(py, xr);
+        const Raw<NW> xs = ld_unit<LD, NW>(px);
+        if (RAWCOPY) st_unit<ST, NW>(py, xs);
         else {
             float f[VEC];
-            unpack_unit<T, NW>(xr, f);
+            unpack_unit<T, NW>(xs, f);
             if constexpr (ADD) {
                 float f2[VEC];
                 unpack_unit<T, NW>(ld_unit<LD, NW>(px2), f2);
@@ -215,6 +247,7 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
     __shared__ double sacc[2][VEC][kColThreads];
     __shared__ int last_flag;
     asm volatile("griddepcontrol.launch_dependents;");
+    LSQ_TRACE(0); LSQ_TRACE_SM();
     const int tx = threadIdx.x % cs.tx, ty = threadIdx.x / cs.tx;
     const long long uc = (long long)blockIdx.x * cs.tx + tx;
     const bool active = uc < cs.units_per_row;
@@ -229,8 +262,10 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
             l2_prefetch(reinterpret_cast<const char*>(cs.g) + pw.off + r * pw.stride);
             if constexpr (ADD) l2_prefetch(reinterpret_cast<const char*>(cs.x2) + pw.off + r * pw.stride);
         }
+        prefetch_params(cs, uc * VEC);
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    LSQ_TRACE(1);
     if (active) {
         ColWalk w;
         w.init(cs, uc, ty, UB);
@@ -238,8 +273,20 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
         const char* __restrict__ pg = reinterpret_cast<const char*>(cs.g) + w.off;
         const char* __restrict__ px2 = ADD ? reinterpret_cast<const char*>(cs.x2) + w.off : nullptr;
         char* __restrict__ pgx = cs.gx ? reinterpret_cast<char*>(cs.gx) + w.off : nullptr;
+        int cnt = w.cnt, since = 0;
+        Raw<NW> xr[kColUnroll], gr[kColUnroll], x2r[ADD ? kColUnroll : 1];
+        auto load_group = [&]() {
+#pragma unroll
+            for (int r = 0; r < kColUnroll; r++) {
+                xr[r] = ld_unit<LD, NW>(px + r * w.stride);
+                if constexpr (ADD) x2r[r] = ld_unit<LD, NW>(px2 + r * w.stride);
+                gr[r] = ld_unit<LD, NW>(pg + r * w.stride);
+            }
+        };
+        // (loads ahead of the parameter request, as the forward does for 16-bit tensors, cost the backward 4 %: 128 registers are full)
         SlotParams<T, MODE, CNW> sp;
         sp.load(cs, uc);
+        LSQ_TRACE(2);
         auto flush = [&]() {
 #pragma unroll
             for (int k = 0; k < VEC; k++) {
@@ -265,15 +312,8 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
                 else st_unit<ST, NW>(dst, pack_unit<T, NW>(fg));
             }
         };
-        int cnt = w.cnt, since = 0;
         for (; cnt >= kColUnroll; cnt -= kColUnroll) {
-            Raw<NW> xr[kColUnroll], gr[kColUnroll], x2r[ADD ? kColUnroll : 1];
-#pragma unroll
-            for (int r = 0; r < kColUnroll; r++) {
-                xr[r] = ld_unit<LD, NW>(px + r * w.stride);
-                if constexpr (ADD) x2r[r] = ld_unit<LD, NW>(px2 + r * w.stride);
-                gr[r] = ld_unit<LD, NW>(pg + r * w.stride);
-            }
+            load_group();
 #pragma unroll
             for (int r = 0; r < kColUnroll; r++) row(xr[r], x2r[ADD ? r : 0], gr[r], pgx ? pgx + r * w.stride : nullptr);
             px += kColUnroll * w.stride; pg += kColUnroll * w.stride;
@@ -282,10 +322,10 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
             if (bmode_reduces(BMODE) && (since += kColUnroll) >= FLUSH_ROWS) { since = 0; flush(); }
         }
         for (; cnt > 0; cnt--) {
-            const Raw<NW> xr = ld_unit<LD, NW>(px), gr = ld_unit<LD, NW>(pg);
-            Raw<NW> x2r;
-            if constexpr (ADD) { x2r = ld_unit<LD, NW>(px2); px2 += w.stride; } else x2r = xr;
-            row(xr, x2r, gr, pgx);
+            const Raw<NW> xs = ld_unit<LD, NW>(px), gsr = ld_unit<LD, NW>(pg);
+            Raw<NW> x2s;
+            if constexpr (ADD) { x2s = ld_unit<LD, NW>(px2); px2 += w.stride; } else x2s = xs;
+            row(xs, x2s, gsr, pgx);
             px += w.stride; pg += w.stride;
             if (pgx) pgx += w.stride;
         }
@@ -305,32 +345,72 @@ lsq_col_bwd_kernel(const __grid_constant__ ColSeg cs) {
             }
         }
     } else {
+    LSQ_TRACE(3);
     __syncthreads();
-    // thread row 0 adds the CTA's thread rows in a fixed order, merges neighbouring slots of the same
-    // channel and issues one fp64 atomic pair per channel run
+    // Thread row 0 adds the CTA's thread rows in a fixed order and merges neighbouring slots of the same channel into runs.
+    // inner >= VEC (7x7, 14x14 maps ...): a unit spans at most two channels, a channel several threads - the runs are parked in the
+    // thread's own shared cells and ONE thread per channel of the CTA adds them in column order (fixed order, no shared atomics:
+    // fp64 atomics on shared memory are CAS loops), so a single fp64 atomic pair per (CTA, channel) reaches L2 instead of one per
+    // (thread, run) - 12x fewer on a 7x7 map, 25x on 14x14.  inner < VEC (channels-last): every run goes straight to L2.
+    const unsigned inner = (unsigned)cs.inner;
+    const bool merge = inner >= (unsigned)VEC;
     if (active && ty == 0) {
-        double rs = 0.0, rb = 0.0;
+        double rs = 0.0, rb = 0.0, hs = 0.0, hb = 0.0;
+        bool tail = false;
 #pragma unroll
         for (int k = 0; k < VEC; k++) {
             for (int r = 0; r < cs.ty; r++) { rs += sacc[0][k][r * cs.tx + tx]; rb += sacc[1][k][r * cs.tx + tx]; }
             const int c = slot_channel(k);
             if (k == VEC - 1 || slot_channel(k + 1 < VEC ? k + 1 : k) != c) {
-                atomicAdd(cs.acc + 2 * (long long)c, rs);
-                atomicAdd(cs.acc + 2 * (long long)c + 1, rb);
-                rs = 0.0; rb = 0.0;
+                if (merge) {
+                    if (!tail) { hs = rs; hb = rb; tail = true; }       // head run; what follows (if anything) is the one tail run
+                } else {
+                    atomicAdd(cs.acc + 2 * (long long)c, rs);
+                    atomicAdd(cs.acc + 2 * (long long)c + 1, rb);
+                }
+                if (k < VEC - 1) { rs = 0.0; rb = 0.0; }
             }
         }
+        if (merge) {
+            const bool two = slot_channel(VEC - 1) != slot_channel(0);
+            sacc[0][0][tx] = hs; sacc[1][0][tx] = hb;                   // this thread's own cells (thread row 0 of column tx)
+            sacc[0][1][tx] = two ? rs : 0.0; sacc[1][1][tx] = two ? rb : 0.0;
+        }
     }
-    __threadfence();
+    if (merge) {
+        __syncthreads();
+        const unsigned u_first = blockIdx.x * (unsigned)cs.tx;
+        unsigned u_last = u_first + (unsigned)cs.tx;
+        if (u_last > (unsigned)cs.units_per_row) u_last = (unsigned)cs.units_per_row;
+        const unsigned c_first = u_first * VEC / inner, c_last = (u_last * VEC - 1u) / inner;
+        for (unsigned c = c_first + threadIdx.x; c <= c_last; c += kColThreads) {
+            const unsigned e0 = c * inner, e1 = e0 + inner - 1u;         // element columns of channel c
+            unsigned u = e0 / VEC, ue = e1 / VEC;
+            if (u < u_first) u = u_first;
+            if (ue > u_last - 1u) ue = u_last - 1u;
+            double s0 = 0.0, b0 = 0.0;
+            for (; u <= ue; u++) {
+                const int j = u * VEC >= e0 ? 0 : 1;                      // the unit starts inside c: head run; before c: tail run
+                s0 += sacc[0][j][u - u_first]; b0 += sacc[1][j][u - u_first];
+            }
+            atomicAdd(cs.acc + 2 * (long long)c, s0);
+            atomicAdd(cs.acc + 2 * (long long)c + 1, b0);
+        }
+    }
+    LSQ_TRACE(4);
+    // release: the barrier orders every thread's atomics before thread 0's fence, the fence before the ticket
     __syncthreads();
     if (threadIdx.x == 0) {
+        fence_acq_rel_gpu();
         const unsigned prev = atomicAdd(cs.counter, 1u);
         last_flag = (prev == cs.total_ctas - 1u);
     }
     __syncthreads();
+    LSQ_TRACE(5);
     if (!last_flag) return;
-    __threadfence();
+    fence_acq_rel_gpu();
     col_finalise<kColThreads>(cs);
+    LSQ_TRACE(6);
     }
 }
 
@@ -500,7 +580,7 @@ lsq_col_bwd_tma_kernel(const __grid_constant__ ColSeg cs) {
         }
     }
     if constexpr (bmode_reduces(BMODE)) {
-        __threadfence();
+        fence_acq_rel_gpu();
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned prev = atomicAdd(cs.counter, 1u);
@@ -508,7 +588,7 @@ lsq_col_bwd_tma_kernel(const __grid_constant__ ColSeg cs) {
         }
         __syncthreads();
         if (!last_flag) return;
-        __threadfence();
+        fence_acq_rel_gpu();
         for (long long c = threadIdx.x; c < cs.C; c += kTmaThreads) {
             const double a = __ldcg(cs.acc + 2 * c), b = __ldcg(cs.acc + 2 * c + 1);
             store_param(cs.gscale, c, cs.pdt, a * cs.gs);

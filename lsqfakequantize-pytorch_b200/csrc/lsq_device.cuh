@@ -384,6 +384,18 @@ __device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
 // drains (DRAM otherwise idle) the kernel's first round of loads is already on its way into L2, so the ramp after the wait starts
 // from L2 latency instead of DRAM latency.  Harmless if the predecessor is still producing the data: L2 is the point of coherence,
 // a later write updates the prefetched line in place and the loads after the wait see it.
+// gpu-scope acquire-release fence for the publish -> ticket -> last-arriver chains: MEMBAR.ALL.GPU, where __threadfence() is the
+// sequentially consistent MEMBAR.SC.GPU (the chains need release / acquire ordering only)
+#ifndef LSQ_LIGHT_FENCE
+#define LSQ_LIGHT_FENCE 1
+#endif
+__device__ __forceinline__ void fence_acq_rel_gpu() {
+#if LSQ_LIGHT_FENCE
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#else
+    __threadfence();
+#endif
+}
 __device__ __forceinline__ void l2_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // A group may walk several CONSECUTIVE tiles (rows of the same weight tensor, as a rule), so
@@ -621,14 +633,14 @@ __device__ __forceinline__ bool channel_finish(const Seg& sg, const TileCtx& tl,
     if (sg.splits == 1) return true;
     if (tg == 0) {
         reinterpret_cast<double2*>(sg.partials)[tl.ltile] = make_double2(a, b);
-        __threadfence();
+        fence_acq_rel_gpu();
         const unsigned prev = atomicAdd(&sg.counters[tl.c], 1u);
         *last_flag = (prev == (unsigned)sg.splits - 1u);
     }
     group_sync<G, THREADS>();
     const bool last = *last_flag != 0;
     if (!last) return false;
-    __threadfence();
+    fence_acq_rel_gpu();
     a = 0.0; b = 0.0;
     // every thread first ISSUES all of its partial-pair loads (one 128-bit L2 read each, four per round: a single-wave
     // launch has <= 4 * G splits), then adds them in index order: one L2 round trip on the launch's critical tail instead
@@ -1560,13 +1572,13 @@ lsq_observe_kernel(const __grid_constant__ Seg single, const Seg* __restrict__ t
         if (tg == 0) {
             sg.partials[2 * tl.ltile] = (double)mn;
             sg.partials[2 * tl.ltile + 1] = (double)mx;
-            __threadfence();
+            fence_acq_rel_gpu();
             const unsigned prev = atomicAdd(&sg.counters[tl.c], 1u);
             last_flag[grp] = (prev == (unsigned)sg.splits - 1u);
         }
         group_sync<G, THREADS>();
         if (!last_flag[grp]) return;
-        __threadfence();
+        fence_acq_rel_gpu();
         mn = __int_as_float(0x7f800000); mx = __int_as_float(0xff800000);
         const double* p = sg.partials + 2 * (tl.c * sg.splits);
         for (int i = tg; i < sg.splits; i += G) { mn = nan_min(mn, (float)__ldcg(p + 2 * i)); mx = nan_max(mx, (float)__ldcg(p + 2 * i + 1)); }

@@ -507,6 +507,33 @@ def test_lean_weight_row_kernels_match_general(dt, shape, native_lib):
     assert torch.allclose(lean[2], general[2], rtol=1e-6, atol=1e-12) and torch.allclose(lean[3], general[3], rtol=1e-6, atol=1e-12)
 
 
+@pytest.mark.parametrize("dt", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("shape_axis", [((64, 512, 7, 7), 1), ((6272, 1024), 1), ((32, 256, 14, 14), 1), ((4099, 96), 1), ((257, 24), 1),
+                                        ((3, 40, 2, 2), 1), ((1031, 8, 3, 3), 1), ((70, 1000, 1, 1), 1), ((9, 333, 4, 4), 1), ((130, 2050, 3, 3), 1)])
+def test_column_backward_epilogue_vs_float64_sums(dt, shape_axis, native_lib):
+    """The column backward's epilogue (per-thread channel runs parked in shared memory, one thread per channel of the CTA adds them,
+    one fp64 atomic pair per (CTA, channel); straight atomics when a unit holds whole channels) on layouts whose channels straddle
+    threads, CTAs and partly filled last CTAs: grad_x bit for bit and grad_scale / grad_shift against the oracle's float64 sums, a
+    second call on the same workspace (accumulators and ticket must come back zeroed) and the call without grad_x."""
+    shape, axis = shape_axis
+    n = int(np.prod(shape))
+    x, g = _mk(n, DT[dt], seed=n % 983, scale=0.7)
+    outer, C, inner = geometry(shape, axis)
+    gen = torch.Generator().manual_seed(C)
+    s = (0.02 + 0.02 * torch.rand(C, generator=gen)).to(U.DEV)
+    b = (-torch.rand(C, generator=gen)).to(U.DEV)
+    q = U.qa(use_gs=False)
+    gx, gs, gb = U.bwd(g, x, s, b, q, outer, C, inner, True)
+    gx2, gs2, gb2 = U.bwd(g, x, s, b, q, outer, C, inner, True)
+    assert torch.equal(gx, gx2) and torch.allclose(gs, gs2, rtol=1e-9, atol=0) and torch.allclose(gb, gb2, rtol=1e-9, atol=0)
+    ogx, ogs, ogb, ms, mb = U.oracle_bwd(g, x, s, b, q, outer, C, inner, True)
+    assert U.same_bits(gx, ogx)
+    U.assert_grads_close(gs, ogs, ms, 1e-5)
+    U.assert_grads_close(gb, ogb, mb, 1e-5)
+    _, gs3, gb3 = U.bwd(g, x, s, b, q, outer, C, inner, True, want_gx=False)
+    assert torch.allclose(gs3, gs, rtol=1e-9, atol=0) and torch.allclose(gb3, gb, rtol=1e-9, atol=0)
+
+
 def test_config4_full_size_gradients_vs_oracle():
     """BASELINE config 4 at FULL size (256x1024x28x28 fp16, per-channel axis 1, grad scaling 1/sqrt(numel*qmax) with the whole
     tensor's numel, lsq_cuda.cu:274): forward and grad_x bit-exact and all 1024 grad_scale / grad_shift values against the
