@@ -128,8 +128,27 @@ int launch(KernelFn k, const Seg& seg, const Seg* table, const int* tile_seg, in
     return 0;
 }
 
-int launch_flat(FlatKernelFn k, const Seg& seg, long long grid, cudaStream_t st) {
+#ifdef LSQ_FLAT_TRACE
+// diagnostic build only: launch i: header (elements, CTAs, 1 fwd / 2 bwd) + four stamps per CTA at buf + i * 8192 * 4 words (tools/flattrace.py); not part of include/lsq_b200.h
+unsigned long long* g_trace_buf = nullptr;
+long long g_trace_launches = 0, g_trace_next = 0;
+}  // namespace
+extern "C" __attribute__((visibility("default"))) long long lsqb200_trace_arm(void* buf, long long launches) {
+    const long long used = g_trace_next;
+    g_trace_buf = reinterpret_cast<unsigned long long*>(buf); g_trace_launches = launches; g_trace_next = 0;
+    return used;
+}
+namespace {
+#endif
+int launch_flat(FlatKernelFn k, const Seg& seg_in, long long grid, cudaStream_t st) {
     if (grid <= 0) return 0;
+#ifdef LSQ_FLAT_TRACE
+    Seg seg = seg_in;
+    seg.stats_out = nullptr;
+    if (g_trace_buf && g_trace_next < g_trace_launches && grid < 8192) seg.stats_out = reinterpret_cast<float*>(g_trace_buf + (g_trace_next++) * 8192 * 4);
+#else
+    const Seg& seg = seg_in;
+#endif
     if (grid > 2147483647LL) return fail(LSQB200_ERR_ARG, "tensor too large for one launch");
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);

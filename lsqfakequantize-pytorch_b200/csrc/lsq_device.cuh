@@ -380,6 +380,15 @@ __device__ __forceinline__ void group_sum2(double& a, double& b, double* sm /* [
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() { pdl_trigger(); pdl_wait(); }
+// diagnostic build (-DLSQ_FLAT_TRACE): per-CTA globaltimer stamps of the lean per-tensor kernels into a caller-provided buffer that
+// the host passes in Seg::stats_out (unused by these kernels); tools/flattrace.py
+#ifdef LSQ_FLAT_TRACE
+#define LSQ_FTRACE(i) do { if (threadIdx.x == 0 && sg.stats_out) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); \
+    unsigned long long* tb_ = reinterpret_cast<unsigned long long*>(sg.stats_out); tb_[(blockIdx.x + 1) * 4 + (i)] = t_; \
+    if ((i) == 0 && blockIdx.x == 0) { tb_[0] = (unsigned long long)sg.inner; tb_[1] = gridDim.x; tb_[2] = sg.g ? 2 : 1; } } } while (0)
+#else
+#define LSQ_FTRACE(i) do {} while (0)
+#endif
 // Non-binding L2 prefetch of the line a thread will load first, issued BEFORE griddepcontrol.wait: while the predecessor's tail
 // drains (DRAM otherwise idle) the kernel's first round of loads is already on its way into L2, so the ramp after the wait starts
 // from L2 latency instead of DRAM latency.  Harmless if the predecessor is still producing the data: L2 is the point of coherence,
@@ -1375,6 +1384,7 @@ lsq_flatfwd_kernel(const __grid_constant__ Seg sg) {
     using Tr = ElemTraits<T>;
     constexpr int NW = 8, VEC = UnitOf<T, NW>::VEC, UB = 32;
     pdl_trigger();
+    LSQ_FTRACE(0);
     const long long units = sg.inner / VEC;
     const long long stride = (long long)gridDim.x * THREADS;
     long long u = (long long)blockIdx.x * THREADS + threadIdx.x;
@@ -1383,6 +1393,7 @@ lsq_flatfwd_kernel(const __grid_constant__ Seg sg) {
     const long long sb = stride * UB;
     if (sg.flags && u < units) l2_prefetch(px);     // one unit: the next one is a whole grid stride away (depth 1 / 2 / 3: 6207 / 6197 / 6153 GB/s on the step)
     pdl_wait();                                   // first touch of tensor / parameter memory is below
+    LSQ_FTRACE(1);
     LazyChan<MODE> lch;
     lch.issue(sg, 0);
     if (blockIdx.x == 0) {                        // the < VEC elements behind the last whole unit
@@ -1404,6 +1415,7 @@ lsq_flatfwd_kernel(const __grid_constant__ Seg sg) {
         }
         px += sb; py += sb;
     }
+    LSQ_FTRACE(2);
 }
 
 template <typename T, int MODE, int BMODE, int THREADS, int LD, int ST, int MINB>
@@ -1414,6 +1426,7 @@ lsq_flatbwd_kernel(const __grid_constant__ Seg sg) {
     __shared__ double red[64];
     __shared__ int last_flag;
     pdl_trigger();
+    LSQ_FTRACE(0);
     const long long units = sg.inner / VEC;
     const long long stride = (long long)gridDim.x * THREADS;
     long long u = (long long)blockIdx.x * THREADS + threadIdx.x;
@@ -1423,6 +1436,7 @@ lsq_flatbwd_kernel(const __grid_constant__ Seg sg) {
     const long long sb = stride * UB;
     if (sg.flags && u < units) { l2_prefetch(px); l2_prefetch(pg); }   // one unit per operand, see lsq_flatfwd_kernel
     pdl_wait();                                   // first touch of tensor / parameter memory is below
+    LSQ_FTRACE(1);
     LazyChan<MODE> lch;
     lch.issue(sg, 0);
     double accS = 0.0, accB = 0.0;
@@ -1453,13 +1467,16 @@ lsq_flatbwd_kernel(const __grid_constant__ Seg sg) {
         accS += (double)ls; accB += (double)lb;
         px += sb; pg += sb;
     }
+    LSQ_FTRACE(2);
     if (!bmode_reduces(BMODE)) {                  // eval: parameters get exact zeros (lsq_kernel.h:143-144)
         if (blockIdx.x == 0 && threadIdx.x == 0) { store_param(sg.gscale, 0, sg.pdt, 0.0); store_param(sg.gshift, 0, sg.pdt, 0.0); }
         return;
     }
     TileCtx tl;
     tl.c = 0; tl.ltile = blockIdx.x; tl.j = (int)blockIdx.x; tl.pidx = 0;
-    if (!channel_finish<THREADS, THREADS>(sg, tl, accS, accB, red, &last_flag, threadIdx.x)) return;
+    const bool fin_ = channel_finish<THREADS, THREADS>(sg, tl, accS, accB, red, &last_flag, threadIdx.x);
+    LSQ_FTRACE(3);
+    if (!fin_) return;
     if (threadIdx.x == 0) {
         store_param(sg.gscale, 0, sg.pdt, accS * sg.gs);
         store_param(sg.gshift, 0, sg.pdt, sg.sym ? 0.0 : accB * sg.gs);
