@@ -126,8 +126,13 @@ struct Tuning {
     // end of the launch (SMs do not progress at the same speed; a single wave of big equal
     // slices costs ~10 %); the backward pays one block reduction + ticket per tile, so its
     // tiles are larger.  Sizes are bytes of ONE operand.
-    int fwd_tile_kb = 64;
-    int bwd_tile_kb = 512;
+    // In-step sweep on the ResNet-50 step (tools/gpu_tilesweep.sh, two alternating rounds per value, +-5 GB/s run to run): forward 128 /
+    // 64 / 48 / 32 / 24 / 16 KB -> 6149 / 6222 / 6257 / 6270-6287 / 6283 / 6256-6312 GB/s; backward 1024 / 512 / 384 / 256 / 192 / 128 / 64 KB
+    // -> 6104 / 6222 / 6253 / 6251-6287 / 6267 / 6246 / 6181 (profiles/r2_tile_sweep.md).  Round 1 sized the tiles on isolated 1 GiB
+    // launches (64 / 512 KB); inside the step smaller tiles shorten each launch's tail of straggling CTAs, which under programmatic
+    // dependent launch is idle time the successor cannot use.
+    int fwd_tile_kb = 32;
+    int bwd_tile_kb = 256;
     int stats_tile_kb = 128;
     // small tensors: shrink tiles until the machine is full - ONE wave of resident CTAs (6 / 4 per SM), not more:
     // in-stream sweep over the ResNet-50 site sizes (tools/site_sweep.py, profiles/r1_site_sweep.md): a second,
