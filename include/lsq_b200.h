@@ -207,6 +207,13 @@ typedef struct lsqb200_optim_args {
 /* params / grads: float[n]; state1: momentum buffer (SGD with momentum) or exp_avg (Adam); state2: exp_avg_sq (Adam) or NULL. */
 LSQB200_API int lsqb200_flat_optimizer_step(float* params, const float* grads, float* state1, float* state2, int64_t n,
                                 const lsqb200_optim_args* args, void* stream);
+/* The same update with torch.optim's PER-PARAMETER step counts (torch/optim/adam.py: `state['step']`, advanced only for parameters
+ * that have a gradient): steps[n] (device, int32, zero-initialised by the caller) is each element's own count - it drives Adam's
+ * bias corrections and the first-step initialisation of SGD's momentum buffer -, and active[n] (device bytes, or NULL = all)
+ * marks the elements that take part in this step; the others keep parameter, state and count.  `args->step` is ignored.  A scale
+ * that only becomes learnable after its observer window (observers.py:455-456) then gets the first step torch.optim gives it. */
+LSQB200_API int lsqb200_flat_optimizer_step_sites(float* params, const float* grads, float* state1, float* state2, int32_t* steps,
+                                      const uint8_t* active, int64_t n, const lsqb200_optim_args* args, void* stream);
 
 /* ---- multi-tensor plans: one launch for many fake-quant sites (the 54 ResNet-50 weights, or
  *      every site of a step).  Semantics per segment are exactly those of the calls above. --- */

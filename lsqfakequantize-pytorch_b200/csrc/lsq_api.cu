@@ -872,6 +872,22 @@ int lsqb200_flat_optimizer_step(float* params, const float* grads, float* state1
     return 0;
 }
 
+int lsqb200_flat_optimizer_step_sites(float* params, const float* grads, float* state1, float* state2, int32_t* steps,
+                                      const uint8_t* active, int64_t n, const lsqb200_optim_args* o, void* stream) {
+    if (!o) return fail(LSQB200_ERR_ARG, "optimizer args are NULL");
+    if (n < 0) return fail(LSQB200_ERR_ARG, "negative size");
+    if (o->kind != LSQB200_OPT_SGD && o->kind != LSQB200_OPT_ADAM) return fail(LSQB200_ERR_ARG, "unknown optimizer kind");
+    if (n == 0) return 0;
+    if (!params || !grads || !steps) return fail(LSQB200_ERR_ARG, "NULL tensor pointer");
+    if (o->kind == LSQB200_OPT_ADAM && (!state1 || !state2)) return fail(LSQB200_ERR_ARG, "Adam needs exp_avg and exp_avg_sq buffers");
+    if (o->kind == LSQB200_OPT_SGD && o->momentum != 0.0 && !state1) return fail(LSQB200_ERR_ARG, "SGD with momentum needs a momentum buffer");
+    if (o->kind == LSQB200_OPT_ADAM && !(o->beta1 >= 0.0 && o->beta1 < 1.0 && o->beta2 >= 0.0 && o->beta2 < 1.0))
+        return fail(LSQB200_ERR_ARG, "Adam betas must lie in [0, 1)");
+    const int e = launch_flat_optim_sites(params, grads, state1, state2, steps, active, n, o, tuning().pdl != 0, (cudaStream_t)stream);
+    if (e != 0) return cuda_fail((cudaError_t)e, "kernel launch");
+    return 0;
+}
+
 int lsqb200_plan_create(const lsqb200_segment* segs, int32_t nseg, lsqb200_plan** out) {
     if (!segs || nseg <= 0 || !out) return fail(LSQB200_ERR_PLAN, "empty segment list");
     lsqb200_plan* p = new lsqb200_plan();

@@ -111,6 +111,8 @@ KernelFn get_observe_kernel(int xdtype, int nw, int group);
 KernelFn get_export_kernel(int xdtype, int mode, int nw, int sem, int dir, int group);
 // kern_optim.cu: fused SGD / Adam step over flat fp32 buffers
 int launch_flat_optim(float* p, const float* g, float* s1, float* s2, long long n, const ::lsqb200_optim_args* o, bool pdl, cudaStream_t st);
+int launch_flat_optim_sites(float* p, const float* g, float* s1, float* s2, int* steps, const unsigned char* active, long long n,
+                            const ::lsqb200_optim_args* o, bool pdl, cudaStream_t st);
 int launch_qparams(const void* scale, const void* shift, float* scale_out, long long* zp_out, long long n, int pdt,
                    float tmin, float tmax, bool pdl, cudaStream_t st);
 

@@ -87,6 +87,8 @@ _PROTOTYPES = {
                                    POINTER(QArgs), c_int, c_int, c_void_p]),
     "lsqb200_qparams": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int64, c_int64, c_void_p]),
     "lsqb200_flat_optimizer_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(OptimArgs), c_void_p]),
+    "lsqb200_flat_optimizer_step_sites": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(OptimArgs),
+                                                  c_void_p]),
     "lsqb200_plan_create": (c_int, [POINTER(Segment), c_int32, POINTER(c_void_p)]),
     "lsqb200_plan_rebind": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                     POINTER(c_void_p), c_void_p]),

@@ -97,7 +97,9 @@ class FlatLSQOptimizer:
     costs one all-reduce (when torch.distributed is initialised; `average=True` folds DDP's 1/world into the update)
     and one kernel launch, whatever the number of fake-quant sites.  The update is torch.optim.SGD's / Adam's
     single-tensor arithmetic in fp32 (csrc/kern_optim.cu).  Parameters that do not require grad (symmetric shifts, static
-    quantizers) keep a zero gradient: with weight_decay = 0 they do not move.
+    quantizers, scales inside their observer window) are skipped - value, optimizer state and step count - as torch.optim skips
+    parameters without a gradient.  (A parameter that requires grad but was not used in this step's forward is NOT skipped: its
+    slice holds zeros, which is a step with a zero gradient.)
 
     Gradient aliasing: every `.grad` is a VIEW of the flat gradient buffer, which is what lets autograd accumulate straight
     into it.  Use `opt.zero_grad()` (zeroes in place).  `model.zero_grad()` / another optimizer's `zero_grad()` default to
@@ -105,10 +107,11 @@ class FlatLSQOptimizer:
     detects that, copies such stray gradients into their slices and re-points `.grad`, so the update is still right (at
     the price of one small copy per affected parameter and step).
 
-    Step counting: ONE counter drives Adam's bias correction and the SGD momentum-buffer initialisation for all parameters.
-    torch.optim skips parameters without a gradient, so its per-parameter counters start when a parameter first receives one
-    (after an observer init window, `scale.requires_grad` is False until then); build this optimizer after the init window -
-    or accept the usual warm-start difference of Adam's bias correction - if that matters.
+    Step counting is torch.optim's: every parameter has its own count (a device int32 per element), advanced only in steps in
+    which the parameter takes part, and it drives Adam's bias corrections and the first-step initialisation of SGD's momentum
+    buffer.  A parameter takes part while it `requires_grad` - torch.optim skips parameters without a gradient, and a quantizer in
+    its observer init window has `scale.requires_grad == False` (observers.py:455-456) -, so a scale that starts learning at
+    batch 1001 gets Adam's first step then, not its 1001st.  The participation mask is rebuilt only when a flag changes.
     """
 
     def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter, Optional[torch.nn.Parameter]]], kind: str = "sgd",
@@ -153,7 +156,10 @@ class FlatLSQOptimizer:
                 self._grad_views.append((shift, self.grads.gshift(name).view_as(shift)))
         self.state1 = torch.zeros_like(self.params) if (kind == "adam" or momentum != 0) else None
         self.state2 = torch.zeros_like(self.params) if kind == "adam" else None
-        self.steps = 0
+        self.steps = 0                                                              # calls of step()
+        self.step_counts = torch.zeros(self.params.numel(), dtype=torch.int32, device=dev)     # per element, as torch.optim's state['step']
+        self._active = torch.ones(self.params.numel(), dtype=torch.uint8, device=dev)
+        self._active_key = None
 
     @classmethod
     def from_model(cls, model: torch.nn.Module, **kw):
@@ -179,9 +185,24 @@ class FlatLSQOptimizer:
                 view.copy_(g.reshape(view.shape))  # autograd accumulated into a fresh tensor: that IS this step's gradient
                 p.grad = view
 
+    def _refresh_active(self):
+        """Elements of parameters that require grad take part in the step (torch.optim: parameters with a gradient)."""
+        key = tuple(p.requires_grad for p, _ in self._grad_views)
+        if key == self._active_key:
+            return
+        mask = torch.zeros(self.params.numel(), dtype=torch.uint8)
+        base = self.grads.flat.data_ptr()
+        for (p, view), on in zip(self._grad_views, key):
+            if on:
+                off = (view.data_ptr() - base) // 4
+                mask[off:off + view.numel()] = 1
+        self._active.copy_(mask)
+        self._active_key = key
+
     def step(self):
         world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
         self._adopt_stray_grads()
+        self._refresh_active()
         self.grads.all_reduce(group=self.group)            # SUM; the 1/world of DDP-style averaging is folded into the update
         self.steps += 1
         a = self._cabi.OptimArgs(float(self.lr), float(self.weight_decay), 1.0 / world if self.average else 1.0, float(self.momentum),
@@ -189,11 +210,11 @@ class FlatLSQOptimizer:
                                  self._cabi.OPT_ADAM if self.kind == "adam" else self._cabi.OPT_SGD, int(self.nesterov))
         dev = self.params.device
         with torch.cuda.device(dev):
-            rc = self._cabi.load().lsqb200_flat_optimizer_step(
+            rc = self._cabi.load().lsqb200_flat_optimizer_step_sites(
                 self.params.data_ptr(), self.grads.flat.data_ptr(), self.state1.data_ptr() if self.state1 is not None else None,
-                self.state2.data_ptr() if self.state2 is not None else None, self.params.numel(), a,
-                torch.cuda.current_stream(dev).cuda_stream)
-        self._cabi.check(rc, "lsqb200_flat_optimizer_step")
+                self.state2.data_ptr() if self.state2 is not None else None, self.step_counts.data_ptr(), self._active.data_ptr(),
+                self.params.numel(), a, torch.cuda.current_stream(dev).cuda_stream)
+        self._cabi.check(rc, "lsqb200_flat_optimizer_step_sites")
 
 
 class _Done:
