@@ -69,3 +69,28 @@ def test_launch_geometry_is_pure_host_logic(native_lib):
     assert info.vec == 4 and info.splits == (1 << 30) // (4096 * 1024)
     assert native_lib.lsqb200_set_tuning(b"bogus=1") == -1
     assert native_lib.lsqb200_set_tuning(None) == 0
+
+
+def test_optimizer_entries_validate_arguments_before_touching_a_device(native_lib):
+    """Argument errors of the two flat-optimizer entries are host logic: they must come back as -1 with a message on a CPU-only
+    box (no launch is attempted), and n == 0 is a no-op."""
+    from torchlsq import _cabi
+    a = _cabi.OptimArgs(0.1, 0.0, 1.0, 0.9, 0.0, 0.9, 0.999, 1e-8, 1, 0, 0)
+    buf = (ctypes.c_float * 8)()
+    cnt = (ctypes.c_int32 * 8)()
+    p, c = ctypes.addressof(buf), ctypes.addressof(cnt)
+    for call in (lambda *r: native_lib.lsqb200_flat_optimizer_step(*r), lambda pp, gg, s1, s2, n, aa, st: native_lib.lsqb200_flat_optimizer_step_sites(pp, gg, s1, s2, c, None, n, aa, st)):
+        a.kind, a.momentum = 0, 0.9
+        assert call(p, p, None, None, 8, a, None) == -1 and b"momentum" in native_lib.lsqb200_last_error()
+        a.kind = 7
+        assert call(p, p, None, None, 8, a, None) == -1 and b"kind" in native_lib.lsqb200_last_error()
+        a.kind = 1
+        assert call(p, p, p, None, 8, a, None) == -1 and b"Adam" in native_lib.lsqb200_last_error()
+        a.beta1 = 1.5
+        assert call(p, p, p, p, 8, a, None) == -1 and b"betas" in native_lib.lsqb200_last_error()
+        a.beta1 = 0.9
+        assert call(p, p, p, p, -1, a, None) == -1
+        assert call(None, None, None, None, 0, a, None) == 0
+        assert call(None, p, p, p, 8, a, None) == -1 and b"NULL" in native_lib.lsqb200_last_error()
+    a.kind = 1
+    assert native_lib.lsqb200_flat_optimizer_step_sites(p, p, p, p, None, None, 8, a, None) == -1      # the step counts are not optional
