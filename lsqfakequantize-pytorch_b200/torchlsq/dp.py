@@ -171,6 +171,35 @@ class FlatLSQOptimizer:
                 found.append((name or "root", sc, sh if isinstance(sh, torch.nn.Parameter) else None))
         return cls(found, **kw)
 
+    def state_dict(self):
+        """Optimizer state for checkpoint / resume (the parameters themselves live in the model's state_dict): the flat momentum /
+        Adam moment buffers and the per-element step counts, keyed by site name so that a model with the same quantizers - in any
+        order - can load it."""
+        out = {"kind": self.kind, "steps": self.steps, "sites": {}}
+        for name, (off, n) in self.grads.offsets.items():
+            sl = slice(off, off + 2 * n)
+            out["sites"][name] = {"step_counts": self.step_counts[sl].clone(),
+                                  "state1": self.state1[sl].clone() if self.state1 is not None else None,
+                                  "state2": self.state2[sl].clone() if self.state2 is not None else None}
+        return out
+
+    def load_state_dict(self, sd):
+        if sd.get("kind") != self.kind:
+            raise ValueError(f"optimizer kind differs: checkpoint {sd.get('kind')!r}, this optimizer {self.kind!r}")
+        missing = [name for name in self.grads.offsets if name not in sd["sites"]]
+        if missing:
+            raise KeyError(f"sites missing from the optimizer checkpoint: {missing[:4]}")
+        self.steps = int(sd.get("steps", 0))
+        for name, (off, n) in self.grads.offsets.items():
+            st = sd["sites"][name]
+            sl = slice(off, off + 2 * n)
+            if st["step_counts"].numel() != 2 * n:
+                raise ValueError(f"site {name!r}: {st['step_counts'].numel() // 2} channels in the checkpoint, {n} here")
+            self.step_counts[sl].copy_(st["step_counts"])
+            for buf, key in ((self.state1, "state1"), (self.state2, "state2")):
+                if buf is not None and st.get(key) is not None:
+                    buf[sl].copy_(st[key])
+
     def zero_grad(self):
         """Zero the flat gradient buffer in place (autograd keeps accumulating into the same slices)."""
         self.grads.zero_()

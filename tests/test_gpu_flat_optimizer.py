@@ -239,6 +239,45 @@ def test_module_training_with_flat_optimizer_matches_torch_optim(kind, kw, tkw):
         assert torch.allclose(a, b, rtol=2e-3, atol=1e-6), float((a - b).abs().max())
 
 
+def test_flat_optimizer_state_dict_resumes_bit_for_bit():
+    """Checkpoint / resume: model state_dict + FlatLSQOptimizer.state_dict() (moments and per-element step counts, keyed by site)
+    loaded into a fresh model and optimizer continue the training with the same bits."""
+    import copy
+    import torch.nn.functional as F
+    torch.backends.cudnn.deterministic = True
+
+    def make():
+        net, data = _net_and_data()
+        other = [p for n, p in net.named_parameters() if not (n.endswith(".scale") or n.endswith(".shift"))]
+        return net, data, torch.optim.SGD(other, lr=0.01, momentum=0.9), FlatLSQOptimizer.from_model(net, kind="adam", lr=0.002)
+
+    def run(net, base, flat, batches):
+        for x, t in batches:
+            loss = F.cross_entropy(net(x), t)
+            base.zero_grad()
+            flat.zero_grad()
+            loss.backward()
+            base.step()
+            flat.step()
+
+    net, data, base, flat = make()
+    run(net, base, flat, data[:3])
+    ck = (copy.deepcopy(net.state_dict()), flat.state_dict(), copy.deepcopy(base.state_dict()))
+    run(net, base, flat, data[3:])
+    want = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net2, _, base2, flat2 = make()
+    net2.load_state_dict(ck[0])
+    flat2.load_state_dict(ck[1])
+    base2.load_state_dict(ck[2])
+    assert all(p.data_ptr() >= flat2.params.data_ptr() for n, p in net2.named_parameters() if n.endswith(".scale"))   # still aliasing the flat buffer
+    run(net2, base2, flat2, data[3:])
+    for k, v in net2.state_dict().items():
+        assert torch.equal(v, want[k]), k
+    assert torch.equal(flat2.step_counts, flat.step_counts)
+    with pytest.raises(ValueError):
+        FlatLSQOptimizer.from_model(net2, kind="sgd", lr=0.1).load_state_dict(ck[1])
+
+
 def test_flat_optimizer_survives_set_to_none_zero_grad():
     """`model.zero_grad()` (set_to_none=True, torch's default) detaches the .grad views from the flat buffer; autograd
     then accumulates into fresh tensors.  step() must fold those back in - the parameters keep learning exactly as with
