@@ -94,3 +94,17 @@ def test_optimizer_entries_validate_arguments_before_touching_a_device(native_li
         assert call(None, p, p, p, 8, a, None) == -1 and b"NULL" in native_lib.lsqb200_last_error()
     a.kind = 1
     assert native_lib.lsqb200_flat_optimizer_step_sites(p, p, p, p, None, None, 8, a, None) == -1      # the step counts are not optional
+
+
+def test_default_tiles_are_the_in_step_sizes(native_lib):
+    """The per-tensor tile sizes were chosen by an in-step sweep (profiles/r2_tile_sweep.md): 32 KB forward and 256 KB backward of
+    one operand, the tile count rounded up to whole waves of resident CTAs and the tile then to whole CTA iterations.  A 205 M-element
+    bf16 site: 12 544 forward tiles of exactly 32 KB, 1731 backward tiles of 232 KB (3 waves of 592)."""
+    from torchlsq import _cabi
+    assert native_lib.lsqb200_set_tuning(None) == 0
+    info = _cabi.LaunchInfo()
+    n = 256 * 64 * 112 * 112
+    assert native_lib.lsqb200_query_launch(1, 1, n, 2, 0, 1, ctypes.byref(info)) == 0
+    assert info.splits == 12544 and info.grid == info.splits
+    assert native_lib.lsqb200_query_launch(1, 1, n, 2, 1, 1, ctypes.byref(info)) == 0
+    assert info.splits == 1731 and 2 * 592 < info.splits <= 3 * 592
